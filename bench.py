@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched quadrotor iLQR hot path on B200.
+
+Metric (BASELINE.json): converged iLQR solves/sec at batch 65536 (config
+"batch 65536 hover problems", N=40 knots, FP64, reference default options), plus the
+amortised microseconds per iLQR iteration.
+
+One "step" = one full batched solve (ILQR::solve, ilqr.hh:53-87, for every problem of the
+batch).  `value` times the device-resident entry point (inputs already in HBM, the timed
+region includes restoring the initial trajectories with a device-to-device copy);
+`e2e` times the reference-facing host entry point qilqr_solve_host with pinned host
+buffers (H2D + AoS->SoA + solve + SoA->AoS + D2H inside the timed region).
+
+N > 1 (torchrun): one process per GPU, each rank solves its own `batch` problems
+(weak scaling, no data-path collective); NCCL only reduces the convergence statistics
+and the max-over-ranks time.
+
+`--impl reference` times the CPU oracle (the restated reference algorithm; the literal
+reference cannot be built here) on all host cores over a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "converged iLQR solves/sec (batch 65536 per GPU, N=40 hover problems, FP64)"
+UNIT = "solves/s"
+N_KNOTS = 40
+# dense as-written FLOPs per knot, counted by the oracle's FLOP-counting scalar
+# (oracle.count_flops on a converged hover trajectory)
+F_BWD, F_ROLL, F_COST = 30231.3, 721.2, 581.2
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def oracle_config(O, m, opts):
+    return O.make_config(mass_kg=m["mass_kg"], inertia=m["inertia"], arm_length_m=m["arm_length_m"],
+                         torque_to_thrust_ratio_m=m["torque_to_thrust_ratio_m"], g_mpss=m["g_mpss"], Q=m["Q"],
+                         R=m["R"], dt_s=m["dt_s"], step_update=opts.line_search_params.step_update,
+                         desired_reduction_frac=opts.line_search_params.desired_reduction_frac,
+                         ls_max_iters=opts.line_search_params.max_iters, rtol=opts.convergence_criteria.rtol,
+                         atol=opts.convergence_criteria.atol, max_iters=opts.convergence_criteria.max_iters)
+
+
+def cpu_initial_trajectories(O, cfg, problems, m, desired, x0):
+    """Open-loop hover rollout of each x0 (the initial trajectory of configs C2/C3) on the CPU."""
+    B = x0.shape[0]
+    out = np.zeros((B, N_KNOTS, 18))
+    zk, zK = np.zeros((N_KNOTS, 4)), np.zeros((N_KNOTS, 4, 12))
+    for b in range(B):
+        seed = problems.constant_state_trajectory(x0[b], N_KNOTS, m["dt_s"], desired[0, 14:18])[0]
+        out[b] = O.forward_sim(cfg, desired, seed, zk, zK)
+    return out
+
+
+def run_cpu_sample(O, cfg, desired, initial, threads):
+    t0 = time.perf_counter()
+    r = O.solve_batch(cfg, desired, initial, nthreads=threads)
+    dt = time.perf_counter() - t0
+    conv = int(np.sum((r["status"] == 1) | (r["status"] == 2)))
+    return dt, conv, int(r["backward_passes"].sum())
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU algorithm (oracle port) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return 0
+    import oracle as O
+    from quadrotorilqr_b200 import problems
+
+    O.build()
+    m, opts = problems.hover_model(), problems.default_options(False)
+    cfg = oracle_config(O, m, opts)
+    cores = O.hardware_threads()
+    sample = int(min(args.batch, max(64, args.cpu_sample_per_core * cores)))
+    desired = problems.hover_desired_trajectory(N_KNOTS, m["dt_s"], m["mass_kg"], m["g_mpss"])
+    x0 = problems.hover_initial_states(sample, seed=args.seed)
+    initial = cpu_initial_trajectories(O, cfg, problems, m, desired, x0)
+    for _ in range(args.warmup):
+        run_cpu_sample(O, cfg, desired, initial[: max(8, sample // 8)], cores)
+    tot_t, tot_conv, tot_it = 0.0, 0, 0
+    for _ in range(args.steps):
+        dt, conv, its = run_cpu_sample(O, cfg, desired, initial, cores)
+        tot_t += dt
+        tot_conv += conv
+        tot_it += its
+    value = tot_conv / tot_t
+    sample_desc = (f"first {sample} problems of the same Philox stream (seed {args.seed}), {args.steps} step(s), "
+                   f"{cores} threads, g++ -O2 -ffp-contract=off")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batch {args.batch} hover problems/GPU, N={N_KNOTS}, dt=0.1, reference default "
+                               "options (rtol=atol=1e-12, max_iters=100), torque_to_thrust_ratio=0.1",
+                   "note": "CPU arm solves a bounded sample of that workload per step"},
+        "us_per_iteration": 1e6 * tot_t / max(1, tot_it),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+
+    from quadrotorilqr_b200 import BatchILQR, RESULT_DTYPE, _capi, problems
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    import ctypes
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world,
+                                device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+
+    m, opts = problems.hover_model(), problems.default_options(False)
+    solver = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
+                       m["Q"], m["R"], m["dt_s"], opts, device=local_rank)
+    solver.set_profiling(True)
+    B, N = args.batch, N_KNOTS
+    stream = torch.cuda.ExternalStream(solver.stream_handle, device=dev)
+
+    # ---- synthetic inputs: this rank's problems [rank*B, (rank+1)*B) of the Philox stream ----
+    desired = problems.hover_desired_trajectory(N, m["dt_s"], m["mass_kg"], m["g_mpss"])
+    x0 = problems.hover_initial_states(B, seed=args.seed, first=rank * B)
+    x0_soa = torch.from_numpy(np.ascontiguousarray(x0.T)).to(dev)  # [13][B]
+    init_soa = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
+    work_soa = torch.empty_like(init_soa)
+    des_aos = torch.from_numpy(desired[None].copy()).to(dev)
+    des_soa = torch.empty((N, 17, 1), dtype=torch.float64, device=dev)
+    res_dev = torch.zeros(B * 24, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    solver.pack_trajectory_device(des_aos, des_soa)
+    solver.rollout_constant_control_device(x0_soa, desired[0, 14:18], init_soa)  # open-loop hover rollout
+    torch.cuda.synchronize()
+
+    def device_step():
+        with torch.cuda.stream(stream):
+            work_soa.copy_(init_soa, non_blocking=True)
+        solver.solve_device(work_soa, des_soa, results=res_dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- `value`: device-resident ----------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = solver.kernel_launch_count
+    bwd_ms = roll_ms = 0.0
+    bwd_knots = roll_knots = prob_iters = prob_rollouts = solver_iters = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        device_step()
+        st = solver.last_solve_stats()
+        bwd_ms += st["backward_ms"]
+        roll_ms += st["rollout_ms"]
+        bwd_knots += st["backward_problem_knots"]
+        roll_knots += st["rollout_problem_knots"]
+        prob_iters += st["problem_iterations"]
+        prob_rollouts += st["problem_rollouts"]
+        solver_iters += st["solver_iterations"]
+    ev1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = solver.kernel_launch_count - launches0
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    res = np.frombuffer(res_dev.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    converged = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
+    ls_failed = int(np.sum(res["status"] == 4))
+    max_iter_hit = int(np.sum(res["status"] == 3))
+
+    # ---- `e2e`: host buffers through qilqr_solve_host ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        init_host = torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True)
+        out_host = torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True)
+        res_host = torch.zeros(B * 24, dtype=torch.uint8, pin_memory=True)
+        aos = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        solver.unpack_trajectory_device(init_soa, aos, time_src=None)
+        torch.cuda.synchronize()
+        init_host.copy_(aos)
+        init_host[:, :, 0] = torch.arange(N, dtype=torch.float64) * m["dt_s"]
+        del aos
+        desired_c = np.ascontiguousarray(desired)
+        e2e_warm = max(1, min(args.warmup, 2))
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_warm):
+            solver.solve_host_buffers(init_host, desired_c, out_host, res_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            solver.solve_host_buffers(init_host, desired_c, out_host, res_host)
+        barrier()
+        e2e_t = time.perf_counter() - t0
+        r2 = np.frombuffer(res_host.numpy().tobytes(), dtype=RESULT_DTYPE)
+        conv2 = int(np.sum((r2["status"] == 1) | (r2["status"] == 2)))
+        e2e = {"t": e2e_t, "steps": e2e_steps, "converged": conv2,
+               "h2d": B * N * 18 * 8 + N * 18 * 8, "d2h": B * N * 18 * 8 + B * 24}
+
+    # ---- reduce over ranks (NCCL: stats and max time only) ---------------------------------------
+    vec = torch.tensor([dev_ms, t_wall * 1e3, float(converged), float(prob_iters), float(ls_failed),
+                        float(max_iter_hit), float(launches), e2e["t"] if e2e else 0.0,
+                        float(e2e["converged"]) if e2e else 0.0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = vec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vec.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
+    else:
+        mx = sm = vec.cpu().numpy()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    step_ms = max(mx[0], 0.0) / args.steps
+    wall_ms = mx[1] / args.steps
+    # device events bracket the stream work; the solver also synchronises with the host every
+    # iteration, so the honest per-step time is the larger of the two clocks
+    ms_per_step = max(step_ms, wall_ms)
+    total_converged_per_step = sm[2]
+    value = total_converged_per_step / (ms_per_step * 1e-3)
+    total_iters = sm[3]
+    us_per_iter = (ms_per_step * 1e3 * world) / max(1.0, total_iters / args.steps) if total_iters else None
+
+    # ---- roofline of the dominant kernel (backward pass), rank 0 -----------------------------------
+    peak = ctypes.c_double(0.0)
+    _capi.lib().qilqr_measure_fp64_peak(ctypes.c_int(local_rank), ctypes.byref(peak))
+    bwd_flops = bwd_knots * F_BWD
+    achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+    roll_achieved = roll_knots * (F_ROLL + F_COST) / (roll_ms * 1e-3) / 1e12 if roll_ms > 0 else None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # algorithmic HBM bytes of the backward kernel: read 17 doubles (+17 desired if per-problem), write 52
+    bwd_bytes = bwd_knots * (17 + 52) * 8.0
+    roofline = {
+        "kernel": "k_backward (ILQR::backwards_pass, linearisation fused into the Riccati sweep)",
+        "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+        "frac": (achieved / peak.value) if (achieved and peak.value) else None,
+        "peak_source": "measured in this run: register-resident DFMA kernel (qilqr_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "flops_per_problem_knot": F_BWD,
+        "flops_definition": "dense as-written reference arithmetic counted by the oracle's FLOP-counting scalar",
+        "traffic": None,
+        "share_of_step": bwd_ms / (ms_per_step * args.steps) if ms_per_step else None,
+        "hbm": {"achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak) if bwd_ms > 0 else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "of fallback"},
+        "rollout_kernel": {"achieved": roll_achieved, "unit": "TFLOP/s", "share_of_step":
+                           roll_ms / (ms_per_step * args.steps) if ms_per_step else None},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batch {B} hover problems/GPU, N={N}, dt=0.1, reference default options "
+                               "(rtol=atol=1e-12, max_iters=100, line search 0.5/0.5/100), "
+                               "torque_to_thrust_ratio=0.1, x0: pos U[-1,1]^3, angle U[0,0.5] rad, vel U[-0.25,0.25]^6 "
+                               f"(Philox seed {args.seed})",
+                   "cache": "inputs larger than L2 (356 MB trajectories + 1.4 GB gains per step vs 126 MB L2)",
+                   "parallelism": f"{world} independent shard(s), one process per GPU"},
+        "us_per_iteration": us_per_iter,
+        "converged_fraction": total_converged_per_step / (B * world),
+        "line_search_failures": int(sm[4]), "max_iters_hit": int(sm[5]),
+        "iterations_per_solve": total_iters / args.steps / (B * world),
+        "solver_iterations_per_step": solver_iters / args.steps,
+        "device_event_ms_per_step": step_ms, "wall_ms_per_step": wall_ms,
+        "gpu_launches": int(sm[6] / world),
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    if e2e:
+        e2e_value = sm[8] / (mx[7] / e2e["steps"])
+        line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * mx[7] / e2e["steps"],
+                       "steps": e2e["steps"],
+                       "api": "qilqr_solve_host (pinned host AoS in/out, results struct per problem)"}
+    if not args.no_cpu_baseline and world >= 1:
+        import oracle as O
+
+        O.build()
+        cfg = oracle_config(O, m, opts)
+        cores = O.hardware_threads()
+        sample = int(min(B, max(64, args.cpu_sample_per_core * cores)))
+        init_cpu = cpu_initial_trajectories(O, cfg, problems, m, desired, x0[:sample])
+        dt, conv, its = run_cpu_sample(O, cfg, desired, init_cpu, cores)
+        line["cpu_baseline"] = {
+            "value": conv / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {sample} problems of the same batch, {cores} threads, oracle (restated reference "
+                      "algorithm, g++ -O2 -ffp-contract=off); the literal reference cannot be built here",
+            "us_per_iteration": 1e6 * dt / max(1, its), "seconds": dt}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

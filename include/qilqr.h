@@ -1,0 +1,222 @@
+/* =============================================================================
+ * include/qilqr.h -- C ABI of libqilqr_b200.so: a batched, B200-native (sm_100a)
+ * replacement for the hot path of nitishthatte/QuadrotorILQR
+ * (ILQR<QuadrotorModel>::solve and the public methods under it).
+ *
+ * The reference has no FFI for this path; its only boundary is the C++ template
+ * ILQR<ModelT> (src/ilqr.hh:25-206) and the pybind module over it
+ * (src/quadrotor_ilqr_binding.cc:20-49).  Each entry point below names the
+ * reference interface it replaces.  One call = a BATCH of independent problems
+ * (the reference solves one per call); batch = 1 reproduces the reference call.
+ *
+ * Conventions
+ *   - all numbers are IEEE double; matrices row-major;
+ *   - state      = 13 doubles  t(3), unit quaternion (x,y,z,w), body velocity
+ *                  lin(3) ang(3)          (QuadrotorModel::State, quadrotor_model.hh:11-14;
+ *                  manif/Eigen coefficient order)
+ *   - tangent    = 12 doubles  pose-lin(3) pose-ang(3) vel-lin(3) vel-ang(3)
+ *                  (QuadrotorModel::StateBlocks, quadrotor_model.hh:29-37)
+ *   - traj point = 18 doubles  time_s, state(13), control(4)   (trajectory.hh:9-14)
+ *   - "_host" entry points take HOST pointers in array-of-structs order
+ *     [batch][knot][18]; they copy to the GPU, run the CUDA kernels and copy
+ *     back.  "_device" entry points take DEVICE pointers in the resident
+ *     structure-of-arrays order described at qilqr_solve_device.
+ *   - every function returns a qilqr_error_t (0 = ok).  Nothing here ever
+ *     computes on the CPU: without a CUDA device qilqr_create fails.
+ * ========================================================================== */
+#ifndef QILQR_H_
+#define QILQR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QILQR_STATE_DIM 12   /* QuadrotorModel::STATE_DIM   quadrotor_model.hh:16 */
+#define QILQR_CONTROL_DIM 4  /* QuadrotorModel::CONTROL_DIM quadrotor_model.hh:40 */
+#define QILQR_STATE_STORAGE 13
+#define QILQR_POINT_STORAGE 18
+#define QILQR_SOA_ROWS 17    /* state(13) + control(4); time_s stays on the host */
+
+typedef enum {
+  QILQR_OK = 0,
+  QILQR_ERR_INVALID_ARGUMENT = 1,
+  QILQR_ERR_INERTIA_NOT_PD = 2,   /* std::runtime_error, quadrotor_model.cc:21-24 */
+  QILQR_ERR_OUT_OF_RANGE = 3,     /* std::out_of_range, cost.hh:39-40 (trajectory longer than desired) */
+  QILQR_ERR_NO_DEVICE = 4,        /* no CUDA device / wrong architecture: there is no CPU fallback */
+  QILQR_ERR_CUDA = 5,
+  QILQR_ERR_OUT_OF_MEMORY = 6,
+  QILQR_ERR_LINE_SEARCH = 7       /* std::runtime_error, ilqr.hh:191-193 (single-problem helpers only) */
+} qilqr_error_t;
+
+/* How one problem's solve() ended (ilqr.hh:53-87). */
+typedef enum {
+  QILQR_STATUS_NOT_RUN = 0,
+  QILQR_STATUS_CONVERGED_EXPECTED = 1, /* exit at ilqr.hh:66-68 (predicted reduction small) */
+  QILQR_STATUS_CONVERGED_ACTUAL = 2,   /* exit at ilqr.hh:82-84 (actual reduction small)    */
+  QILQR_STATUS_MAX_ITERS = 3,          /* loop bound, ilqr.hh:58,86                          */
+  QILQR_STATUS_LINE_SEARCH_FAILED = 4  /* the reference throws here, ilqr.hh:191-193; also
+                                          how NaN/Inf costs surface                          */
+} qilqr_status_t;
+
+/* QuadrotorModel constructor arguments (quadrotor_model.hh:8-10). */
+typedef struct {
+  double mass_kg;
+  double inertia[9];
+  double arm_length_m;
+  double torque_to_thrust_ratio_m;
+  double g_mpss;
+} qilqr_model_t;
+
+/* ILQROptions, field for field (ilqr_options.hh:4-22), followed by batch-only
+ * extensions whose zero value reproduces the reference. */
+typedef struct {
+  /* LineSearchParams */
+  double step_update;
+  double desired_reduction_frac;
+  int32_t line_search_max_iters;
+  int32_t populate_debug; /* bool ILQROptions::populate_debug */
+  /* ConvergenceCriteria */
+  double rtol;
+  double atol;
+  double max_iters; /* a double in the reference (ilqr_options.hh:14) */
+  /* extensions */
+  int32_t symmetrize_vxx;      /* V_xx <- (V_xx + V_xx^T)/2 after ilqr.hh:133 (needed for long horizons) */
+  int32_t num_parallel_alphas; /* 0/1: sequential backtracking; P>1: P step sizes per round as
+                                  parallel rollouts, first passing one wins (same result) */
+  double quu_regularization;   /* Q_uu += mu*I before ilqr.hh:126; 0 = reference */
+} qilqr_options_t;
+
+/* Per-problem outcome of a solve. */
+typedef struct {
+  int32_t status;          /* qilqr_status_t */
+  int32_t backward_passes; /* calls of backwards_pass (ilqr.hh:59) */
+  int32_t rollouts;        /* calls of forward_sim (ilqr.hh:71,180) */
+  int32_t num_debug;       /* completed iterations = ILQRDebug entries (ilqr.hh:78-80) */
+  double final_cost;       /* cost of the returned trajectory */
+} qilqr_result_t;
+
+typedef struct qilqr_solver qilqr_solver_t;
+
+/* ILQR<QuadrotorModel>{model, CostFunction{Q, R, .}, dt_s, options} (ilqr.hh:27-32,
+ * quadrotor_ilqr_binding.cc:20-32).  The desired trajectory, which the reference's
+ * CostFunction owns (cost.hh:30-34), is an argument of each call instead so that
+ * every problem of a batch may have its own.  `device` = CUDA ordinal. */
+int qilqr_create(const qilqr_model_t *model, const double *Q /*[144]*/, const double *R /*[16]*/,
+                 double dt_s, const qilqr_options_t *options, int device, qilqr_solver_t **out);
+void qilqr_destroy(qilqr_solver_t *solver);
+int qilqr_set_options(qilqr_solver_t *solver, const qilqr_options_t *options);
+const char *qilqr_error_string(int err);
+const char *qilqr_last_error_message(const qilqr_solver_t *solver);
+/* Number of this library's kernels launched by the solver so far (for bench.py's gpu_launches). */
+int64_t qilqr_kernel_launch_count(const qilqr_solver_t *solver);
+/* The CUDA stream (cudaStream_t) the solver launches on, for event timing by the caller. */
+void *qilqr_stream(const qilqr_solver_t *solver);
+
+/* ---------------------------------------------------------------------------
+ * Host-buffer entry points (array-of-structs).  desired_count is 1 (one desired
+ * trajectory shared by the whole batch) or batch.
+ * ------------------------------------------------------------------------- */
+
+/* ILQR::solve (ilqr.hh:53-87) for `batch` problems of `n_knots` knots.
+ *   out_k [batch][n][4], out_K [batch][n][4][12]: gains of the last backward pass (NULL to skip)
+ *   cost_hist [batch][hist_cap]: new_cost after each completed iteration (NULL to skip)
+ *   debug_traj [batch][debug_cap][n][18]: ILQRDebug trajectories (ilqr_debug.hh:9-22); needs
+ *     populate_debug and debug_cap >= ceil(max_iters) (NULL to skip)
+ *   results [batch]. */
+int qilqr_solve_host(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                     int desired_count, const double *initial, double *out_traj, double *out_k,
+                     double *out_K, double *cost_hist, int hist_cap, double *debug_traj,
+                     int debug_cap, qilqr_result_t *results);
+
+/* ILQR::forward_sim (ilqr.hh:149-172): alpha [batch]. */
+int qilqr_forward_sim_host(qilqr_solver_t *solver, int batch, int n_knots, const double *current,
+                           const double *k, const double *K, const double *alpha, double *out_traj);
+/* ILQR::cost_trajectory (ilqr.hh:89-95): cost [batch].  n_desired_knots < n_knots ->
+ * QILQR_ERR_OUT_OF_RANGE (cost.hh:39-40). */
+int qilqr_cost_trajectory_host(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                               int desired_count, int n_desired_knots, const double *traj,
+                               double *cost);
+/* ILQR::backwards_pass (ilqr.hh:97-147): k [batch][n][4], K [batch][n][4][12],
+ * terms [batch][2] = {QuTk, kTQuuk} (detail::CostReductionTerms, ilqr.hh:13-16). */
+int qilqr_backwards_pass_host(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                              int desired_count, const double *traj, double *k, double *K,
+                              double *terms);
+/* ILQR::line_search (ilqr.hh:174-194): per problem new trajectory, cost, accepted step and
+ * status[b] = 0 or QILQR_ERR_LINE_SEARCH. */
+int qilqr_line_search_host(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                           int desired_count, const double *current, const double *current_cost,
+                           const double *k, const double *K, const double *terms, double *out_traj,
+                           double *new_cost, double *step, int32_t *status);
+
+/* QuadrotorModel::discrete_dynamics (quadrotor_model.cc:33-49): x [batch][13], u [batch][4] ->
+ * x_next [batch][13], J_x [batch][144], J_u [batch][48] (either may be NULL). */
+int qilqr_discrete_dynamics_host(qilqr_solver_t *solver, int batch, const double *x, const double *u,
+                                 double *x_next, double *J_x, double *J_u);
+/* QuadrotorModel::continuous_dynamics (quadrotor_model.cc:65-122): xdot [batch][12]. */
+int qilqr_continuous_dynamics_host(qilqr_solver_t *solver, int batch, const double *x,
+                                   const double *u, double *xdot, double *J_x, double *J_u);
+/* minus(State, State, diffs) (quadrotor_model.cc:215-250): out [batch][12],
+ * J_lhs/J_rhs [batch][144] (may be NULL). */
+int qilqr_state_minus_host(qilqr_solver_t *solver, int batch, const double *lhs, const double *rhs,
+                           double *out, double *J_lhs, double *J_rhs);
+/* add(State, StateTangent, diffs) (quadrotor_model.cc:174-206): out [batch][13]. */
+int qilqr_state_add_host(qilqr_solver_t *solver, int batch, const double *x, const double *tangent,
+                         double *out, double *J_lhs, double *J_rhs);
+/* CostFunction::operator() (cost.hh:36-61): cost [batch], C_x [batch][12], C_u [batch][4],
+ * C_xx [batch][144], C_uu [batch][16], C_xu [batch][48] (derivatives may be NULL). */
+int qilqr_cost_host(qilqr_solver_t *solver, int batch, const double *x, const double *u,
+                    const double *x_d, const double *u_d, double *cost, double *C_x, double *C_u,
+                    double *C_xx, double *C_uu, double *C_xu);
+
+/* ---------------------------------------------------------------------------
+ * Device-resident entry points (structure-of-arrays, problem index fastest):
+ *   trajectory  double[n_knots][17][batch]   rows 0-12 state, 13-16 control
+ *   desired     double[n_knots][17][desired_count]  (desired_count = 1 or batch)
+ *   k           double[n_knots][4][batch]
+ *   K           double[n_knots][48][batch]   row = 12*control + state
+ *   cost_hist   double[hist_cap][batch]
+ * All pointers are device pointers on the solver's device; calls are asynchronous
+ * on qilqr_stream() except that qilqr_solve_device returns after the last
+ * iteration has been issued and its results are complete on the stream.
+ * ------------------------------------------------------------------------- */
+int qilqr_solve_device(qilqr_solver_t *solver, int batch, int n_knots, const double *d_desired,
+                       int desired_count, double *d_traj_inout, double *d_k, double *d_K,
+                       double *d_cost_hist, int hist_cap, qilqr_result_t *d_results);
+/* AoS <-> SoA transposition kernels (device to device). */
+int qilqr_pack_trajectory_device(qilqr_solver_t *solver, int batch, int n_knots,
+                                 const double *d_aos /*[batch][n][18]*/, double *d_soa);
+int qilqr_unpack_trajectory_device(qilqr_solver_t *solver, int batch, int n_knots,
+                                   const double *d_soa, const double *d_time_aos_or_null,
+                                   double *d_aos);
+/* Open-loop rollout helper: x0 [13][batch] (SoA), u_const[4] -> trajectory SoA. */
+int qilqr_rollout_constant_control_device(qilqr_solver_t *solver, int batch, int n_knots,
+                                          const double *d_x0_soa, const double *u_const /*host[4]*/,
+                                          double *d_traj_soa);
+
+/* Aggregate counters of the last qilqr_solve_* call. */
+typedef struct {
+  int64_t solver_iterations;   /* outer iterations issued (max over problems) */
+  int64_t problem_iterations;  /* sum over problems of backward passes */
+  int64_t problem_rollouts;    /* sum over problems of rollouts */
+  int64_t kernel_launches;     /* kernels launched by this call */
+  double backward_ms;          /* CUDA-event time spent in backward-pass kernels */
+  double rollout_ms;           /* CUDA-event time spent in rollout/line-search kernels */
+  int64_t backward_problem_knots; /* problem-knots processed by backward kernels */
+  int64_t rollout_problem_knots;  /* problem-knots processed by rollout kernels */
+} qilqr_solve_stats_t;
+int qilqr_last_solve_stats(const qilqr_solver_t *solver, qilqr_solve_stats_t *out);
+/* Enable/disable per-kernel CUDA-event timing (adds a few microseconds per launch). */
+int qilqr_set_profiling(qilqr_solver_t *solver, int enabled);
+
+
+/* Measurement aid for the roofline denominator: sustained FP64 FMA throughput of `device`
+ * in TFLOP/s (2 flops per DFMA), from a register-resident DFMA kernel timed with CUDA events. */
+int qilqr_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QILQR_H_ */

@@ -1,0 +1,862 @@
+// =============================================================================
+// qilqr_capi.cu -- host side of libqilqr_b200.so: the C ABI of include/qilqr.h.
+// Owns the device workspace, drives ILQR::solve's control flow (ilqr.hh:53-87)
+// for a whole batch with per-problem termination, and offers the reference's
+// public methods as batched calls.  No CPU fallback: every entry point launches
+// CUDA kernels or fails.
+// =============================================================================
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qilqr_api_kernels.cuh"
+#include "qilqr_kernels.cuh"
+
+using namespace qilqr;
+
+namespace {
+
+struct DeviceBuffer {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+struct TimedSpan {
+  cudaEvent_t start, stop;
+  int kind;  // 0 backward, 1 rollout
+};
+
+}  // namespace
+
+struct qilqr_solver {
+  DeviceParams p{};
+  qilqr_options_t opt{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  int64_t launches = 0;
+  qilqr_solve_stats_t stats{};
+  bool profiling = false;
+  std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+
+  // workspace
+  DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
+      hist_d, debug_d, misc;
+  int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
+  int *d_counts = nullptr;
+};
+
+namespace {
+
+#define QCUDA(S, expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      (S)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+      return (e__ == cudaErrorMemoryAllocation) ? QILQR_ERR_OUT_OF_MEMORY : QILQR_ERR_CUDA;       \
+    }                                                                                             \
+  } while (0)
+
+int fail(qilqr_solver *S, int code, const char *msg) {
+  if (S) S->last_error = msg;
+  return code;
+}
+
+cudaEvent_t get_event(qilqr_solver *S) {
+  if (!S->event_pool.empty()) {
+    cudaEvent_t e = S->event_pool.back();
+    S->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct SpanGuard {
+  qilqr_solver *S;
+  TimedSpan sp{};
+  bool on;
+  SpanGuard(qilqr_solver *s, int kind) : S(s), on(s->profiling) {
+    if (on) {
+      sp.start = get_event(S);
+      sp.stop = get_event(S);
+      sp.kind = kind;
+      cudaEventRecord(sp.start, S->stream);
+    }
+  }
+  ~SpanGuard() {
+    if (on) {
+      cudaEventRecord(sp.stop, S->stream);
+      S->spans.push_back(sp);
+    }
+  }
+};
+void drain_spans(qilqr_solver *S) {  // call after a stream synchronise
+  for (auto &sp : S->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sp.start, sp.stop);
+    (sp.kind == 0 ? S->stats.backward_ms : S->stats.rollout_ms) += ms;
+    S->event_pool.push_back(sp.start);
+    S->event_pool.push_back(sp.stop);
+  }
+  S->spans.clear();
+}
+
+void apply_options(qilqr_solver *S) {
+  S->p.step_update = S->opt.step_update;
+  S->p.desired_reduction_frac = S->opt.desired_reduction_frac;
+  S->p.rtol = S->opt.rtol;
+  S->p.atol = S->opt.atol;
+  S->p.max_iters = S->opt.max_iters;
+  S->p.quu_reg = S->opt.quu_regularization;
+  S->p.ls_max_iters = S->opt.line_search_max_iters;
+  S->p.symmetrize_vxx = S->opt.symmetrize_vxx;
+}
+
+// Eigen::LLT<Matrix3d> of the inertia + the isApprox(transpose) test (quadrotor_model.cc:20-24)
+bool factor_inertia(const double *I, double *L) {
+  for (int i = 0; i < 9; ++i) L[i] = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    double x = I[4 * k];
+    for (int j = 0; j < k; ++j) x -= L[3 * k + j] * L[3 * k + j];
+    if (!(x > 0.0)) return false;
+    x = std::sqrt(x);
+    L[4 * k] = x;
+    for (int i = k + 1; i < 3; ++i) {
+      double s = I[3 * i + k];
+      for (int j = 0; j < k; ++j) s -= L[3 * i + j] * L[3 * k + j];
+      L[3 * i + k] = s / x;
+    }
+  }
+  double d2 = 0, n2 = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double d = I[3 * i + j] - I[3 * j + i];
+      d2 += d * d;
+      n2 += I[3 * i + j] * I[3 * i + j];
+    }
+  return d2 <= 1e-24 * n2;
+}
+void llt_solve(const double *L, const double *b, double *x) {
+  double y[3];
+  y[0] = b[0] / L[0];
+  y[1] = (b[1] - L[3] * y[0]) / L[4];
+  y[2] = (b[2] - L[6] * y[0] - L[7] * y[1]) / L[8];
+  x[2] = y[2] / L[8];
+  x[1] = (y[1] - L[7] * x[2]) / L[4];
+  x[0] = (y[0] - L[3] * x[1] - L[6] * x[2]) / L[0];
+}
+
+struct StateLayout {  // carve SolveState out of two flat buffers
+  static constexpr int kDoubles = 5, kInts = 8;
+};
+SolveState make_state(qilqr_solver *S, int B, double *hist, int hist_cap) {
+  double *d = S->state_d.as<double>();
+  int *i = S->state_i.as<int>();
+  SolveState st;
+  st.cost = d; st.new_cost = d + B; st.qutk = d + 2 * size_t(B); st.ktquuk = d + 3 * size_t(B); st.alpha = d + 4 * size_t(B);
+  st.ls_iter = i; st.status = i + B; st.bwd = i + 2 * size_t(B); st.rollouts = i + 3 * size_t(B);
+  st.ndebug = i + 4 * size_t(B); st.sel = i + 5 * size_t(B); st.phase = i + 6 * size_t(B);
+  st.accepted_iter = i + 7 * size_t(B);
+  st.cost_hist = hist;
+  st.hist_cap = hist_cap;
+  return st;
+}
+int ensure_state(qilqr_solver *S, int B) {
+  QCUDA(S, S->state_d.ensure(sizeof(double) * StateLayout::kDoubles * size_t(B)));
+  QCUDA(S, S->state_i.ensure(sizeof(int) * StateLayout::kInts * size_t(B)));
+  QCUDA(S, S->lists.ensure(sizeof(int) * 4 * size_t(B)));
+  return QILQR_OK;
+}
+
+inline unsigned blocks_for(int n, int per) { return unsigned((n + per - 1) / per); }
+
+// ---------------------------------------------------------------------------
+// The batched solve loop (device-resident data).
+// ---------------------------------------------------------------------------
+int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, double *d_traj, double *d_k,
+               double *d_K, double *d_hist, int hist_cap, qilqr_result_t *d_results, double *d_debug,
+               int debug_cap) {
+  if (B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "bad batch/knots/desired_count");
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = ensure_state(S, B);
+  if (rc) return rc;
+  QCUDA(S, S->buf1.ensure(sizeof(double) * size_t(N) * 17 * B));
+  if (!d_k) {
+    QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B));
+    d_k = S->gk.as<double>();
+  }
+  if (!d_K) {
+    QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
+    d_K = S->gK.as<double>();
+  }
+  cudaStream_t st_ = S->stream;
+  Problem pr{B, N, Bd, d_traj, S->buf1.as<double>(), d_desired, d_k, d_K};
+  SolveState st = make_state(S, B, d_hist, d_hist ? hist_cap : 0);
+  int *listA[2] = {S->lists.as<int>(), S->lists.as<int>() + B};
+  int *listS[2] = {S->lists.as<int>() + 2 * size_t(B), S->lists.as<int>() + 3 * size_t(B)};
+
+  S->stats = qilqr_solve_stats_t{};
+  const int64_t launches0 = S->launches;
+
+  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B);
+  k_cost_trajectory<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, d_traj, d_desired, B, N, Bd, st.cost);
+  S->launches += 2;
+
+  const bool capture_debug = S->opt.populate_debug && d_debug && debug_cap > 0;
+  int n_active = B;
+  const int *active = nullptr;  // nullptr = identity list
+  int cur = 0;
+  for (int i = 0; i < S->opt.max_iters && n_active > 0; ++i) {  // ilqr.hh:58 (max_iters is a double)
+    BackwardArgs ba{pr, st, active, n_active, i, 1, nullptr, nullptr};
+    {
+      SpanGuard g(S, 0);
+      k_backward_t1<<<blocks_for(n_active, 64), 64, 0, st_>>>(S->p, ba);
+    }
+    S->stats.backward_problem_knots += int64_t(n_active) * N;
+    S->stats.problem_iterations += n_active;
+    k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
+    S->launches += 2;
+    QCUDA(S, cudaStreamSynchronize(st_));
+    int n_search = S->h_counts[0];
+    int n_next = 0;
+    int s = 0, rounds = 0;
+    while (n_search > 0) {
+      RolloutArgs ra{pr, st, listS[s], n_search, i, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr};
+      {
+        SpanGuard g(S, 1);
+        k_rollout<<<blocks_for(n_search, 128), 128, 0, st_>>>(S->p, ra);
+      }
+      S->stats.rollout_problem_knots += int64_t(n_search) * N;
+      S->stats.problem_rollouts += n_search;
+      ++S->launches;
+      if (capture_debug) {
+        dim3 grid(blocks_for(n_search, 128), 32);
+        k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, listS[s], n_search, i, d_debug, debug_cap);
+        ++S->launches;
+      }
+      k_compact<<<1, 1024, 0, st_>>>(listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur], S->d_counts);
+      ++S->launches;
+      QCUDA(S, cudaStreamSynchronize(st_));
+      n_search = S->h_counts[0];
+      n_next = S->h_counts[1];
+      s = 1 - s;
+      ++rounds;
+    }
+    if (rounds > 1) {  // rebuild the ordered active list from this iteration's list
+      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
+      ++S->launches;
+      QCUDA(S, cudaStreamSynchronize(st_));
+      n_next = S->h_counts[1];
+    }
+    drain_spans(S);
+    ++S->stats.solver_iterations;
+    cur = 1 - cur;
+    active = listA[cur];
+    n_active = n_next;
+  }
+  k_finalize<<<blocks_for(B, 256), 256, 0, st_>>>(st, B, d_results);
+  {
+    dim3 grid(blocks_for(B, 128), 64);
+    k_collect<<<grid, 128, 0, st_>>>(pr, st.sel);
+  }
+  S->launches += 2;
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaGetLastError());
+  S->stats.kernel_launches = S->launches - launches0;
+  return QILQR_OK;
+}
+
+int pack_traj(qilqr_solver *S, int B, int N, const double *d_aos, double *d_soa) {
+  dim3 grid(blocks_for(B, 32), unsigned(N < 64 ? N : 64));
+  k_pack<<<grid, 576, 0, S->stream>>>(d_aos, d_soa, B, N);
+  ++S->launches;
+  return QILQR_OK;
+}
+int unpack_traj(qilqr_solver *S, int B, int N, const double *d_soa, double *d_aos) {
+  dim3 grid(blocks_for(B, 32), unsigned(N < 64 ? N : 64));
+  k_unpack<<<grid, 576, 0, S->stream>>>(d_soa, d_aos, B, N);
+  ++S->launches;
+  return QILQR_OK;
+}
+int transpose_to_soa(qilqr_solver *S, const double *in, double *out, int B, int N, int W) {
+  const size_t total = size_t(B) * N * W;
+  const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, 148 * 16));
+  k_transpose_bnw_to_nwb<<<blocks, 256, 0, S->stream>>>(in, out, B, N, W);
+  ++S->launches;
+  return QILQR_OK;
+}
+int transpose_to_aos(qilqr_solver *S, const double *in, double *out, int B, int N, int W) {
+  const size_t total = size_t(B) * N * W;
+  const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, 148 * 16));
+  k_transpose_nwb_to_bnw<<<blocks, 256, 0, S->stream>>>(in, out, B, N, W);
+  ++S->launches;
+  return QILQR_OK;
+}
+
+// Upload an AoS host trajectory batch and pack it to SoA.
+int upload_traj(qilqr_solver *S, DeviceBuffer &stage, int B, int N, const double *h_aos, double *d_soa) {
+  const size_t bytes = sizeof(double) * size_t(B) * N * 18;
+  QCUDA(S, stage.ensure(bytes));
+  QCUDA(S, cudaMemcpyAsync(stage.ptr, h_aos, bytes, cudaMemcpyHostToDevice, S->stream));
+  return pack_traj(S, B, N, stage.as<double>(), d_soa);
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+const char *qilqr_error_string(int err) {
+  switch (err) {
+    case QILQR_OK: return "ok";
+    case QILQR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case QILQR_ERR_INERTIA_NOT_PD: return "Inertia matrix is not positive definite!";
+    case QILQR_ERR_OUT_OF_RANGE: return "trajectory longer than the desired trajectory";
+    case QILQR_ERR_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU fallback)";
+    case QILQR_ERR_CUDA: return "CUDA error";
+    case QILQR_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case QILQR_ERR_LINE_SEARCH: return "Reached maximum number of line search iterations";
+    default: return "unknown error";
+  }
+}
+
+int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, double dt_s,
+                 const qilqr_options_t *options, int device, qilqr_solver_t **out) {
+  if (!model || !Q || !R || !options || !out) return QILQR_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  DeviceParams p{};
+  if (!factor_inertia(model->inertia, p.L)) return QILQR_ERR_INERTIA_NOT_PD;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return QILQR_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return QILQR_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return QILQR_ERR_NO_DEVICE;
+
+  qilqr_solver *S = new qilqr_solver();
+  S->device = device;
+  p.mass = model->mass_kg;
+  p.g = model->g_mpss;
+  p.dt = dt_s;
+  for (int i = 0; i < 9; ++i) p.inertia[i] = model->inertia[i];
+  for (int i = 0; i < 3; ++i) p.Linv[i] = 1.0 / p.L[4 * i];
+  const double a = model->arm_length_m, r = model->torque_to_thrust_ratio_m;
+  const double ma[12] = {0, -a, 0, a, a, 0.0, -a, 0.0, -r, r, -r, r};  // quadrotor_model.cc:15-18
+  for (int i = 0; i < 12; ++i) p.moment_arms[i] = ma[i];
+  for (int j = 0; j < 4; ++j) {
+    p.JuC[j] = 1.0 / model->mass_kg;  // quadrotor_model.cc:115-116
+    const double col[3] = {ma[j], ma[4 + j], ma[8 + j]};
+    double sol[3];
+    llt_solve(p.L, col, sol);  // quadrotor_model.cc:118-119
+    for (int i = 0; i < 3; ++i) p.JuC[4 * (1 + i) + j] = sol[i];
+  }
+  for (int i = 0; i < 16; ++i) p.Bu[i] = dt_s * p.JuC[i];
+  for (int i = 0; i < 144; ++i) p.Q[i] = Q[i];
+  for (int i = 0; i < 16; ++i) p.R[i] = R[i];
+  S->p = p;
+  S->opt = *options;
+  apply_options(S);
+  if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void **>(&S->h_counts), 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void **>(&S->d_counts), S->h_counts, 0) != cudaSuccess) {
+    delete S;
+    return QILQR_ERR_CUDA;
+  }
+  *out = S;
+  return QILQR_OK;
+}
+
+void qilqr_destroy(qilqr_solver_t *S) {
+  if (!S) return;
+  cudaSetDevice(S->device);
+  cudaStreamSynchronize(S->stream);
+  for (DeviceBuffer *b : {&S->buf1, &S->gk, &S->gK, &S->state_d, &S->state_i, &S->lists, &S->desired_soa,
+                          &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
+                          &S->debug_d, &S->misc})
+    b->release();
+  for (auto e : S->event_pool) cudaEventDestroy(e);
+  if (S->h_counts) cudaFreeHost(S->h_counts);
+  if (S->stream) cudaStreamDestroy(S->stream);
+  delete S;
+}
+
+int qilqr_set_options(qilqr_solver_t *S, const qilqr_options_t *options) {
+  if (!S || !options) return QILQR_ERR_INVALID_ARGUMENT;
+  S->opt = *options;
+  apply_options(S);
+  return QILQR_OK;
+}
+const char *qilqr_last_error_message(const qilqr_solver_t *S) { return S ? S->last_error.c_str() : ""; }
+int64_t qilqr_kernel_launch_count(const qilqr_solver_t *S) { return S ? S->launches : 0; }
+void *qilqr_stream(const qilqr_solver_t *S) { return S ? static_cast<void *>(S->stream) : nullptr; }
+int qilqr_last_solve_stats(const qilqr_solver_t *S, qilqr_solve_stats_t *out) {
+  if (!S || !out) return QILQR_ERR_INVALID_ARGUMENT;
+  *out = S->stats;
+  return QILQR_OK;
+}
+int qilqr_set_profiling(qilqr_solver_t *S, int enabled) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  S->profiling = enabled != 0;
+  return QILQR_OK;
+}
+
+// ---- device-resident API ------------------------------------------------------
+int qilqr_solve_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_desired, int desired_count,
+                       double *d_traj_inout, double *d_k, double *d_K, double *d_cost_hist, int hist_cap,
+                       qilqr_result_t *d_results) {
+  if (!S || !d_desired || !d_traj_inout) return QILQR_ERR_INVALID_ARGUMENT;
+  return solve_core(S, batch, n_knots, d_desired, desired_count, d_traj_inout, d_k, d_K, d_cost_hist, hist_cap,
+                    d_results, nullptr, 0);
+}
+int qilqr_pack_trajectory_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_aos, double *d_soa) {
+  if (!S || !d_aos || !d_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  return pack_traj(S, batch, n_knots, d_aos, d_soa);
+}
+int qilqr_unpack_trajectory_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_soa,
+                                   const double *d_time_aos, double *d_aos) {
+  if (!S || !d_aos || !d_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  const size_t bytes = sizeof(double) * size_t(batch) * n_knots * 18;
+  if (d_time_aos && d_time_aos != d_aos)
+    QCUDA(S, cudaMemcpyAsync(d_aos, d_time_aos, bytes, cudaMemcpyDeviceToDevice, S->stream));
+  else if (!d_time_aos)
+    QCUDA(S, cudaMemsetAsync(d_aos, 0, bytes, S->stream));
+  return unpack_traj(S, batch, n_knots, d_soa, d_aos);
+}
+int qilqr_rollout_constant_control_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_x0_soa,
+                                          const double *u, double *d_traj_soa) {
+  if (!S || !d_x0_soa || !u || !d_traj_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  k_rollout_constant<<<blocks_for(batch, 128), 128, 0, S->stream>>>(S->p, d_x0_soa, u[0], u[1], u[2], u[3],
+                                                                   d_traj_soa, batch, n_knots);
+  ++S->launches;
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+// ---- host-buffer API -----------------------------------------------------------
+int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *initial,
+                     double *out_traj, double *out_k, double *out_K, double *cost_hist, int hist_cap,
+                     double *debug_traj, int debug_cap, qilqr_result_t *results) {
+  if (!S || !desired || !initial || !out_traj) return QILQR_ERR_INVALID_ARGUMENT;
+  if (B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "bad batch/knots/desired_count");
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->stream;
+  const size_t traj_bytes = sizeof(double) * size_t(B) * N * 18;
+  QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(N) * 17 * Bd));
+  int rc = upload_traj(S, S->stage_b, Bd, N, desired, S->desired_soa.as<double>());
+  if (rc) return rc;
+  rc = upload_traj(S, S->stage_a, B, N, initial, S->traj_soa.as<double>());
+  if (rc) return rc;
+  double *d_k = nullptr, *d_K = nullptr, *d_hist = nullptr, *d_debug = nullptr;
+  if (out_k) { QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B)); d_k = S->gk.as<double>(); }
+  if (out_K) { QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B)); d_K = S->gK.as<double>(); }
+  if (cost_hist && hist_cap > 0) {
+    QCUDA(S, S->hist_d.ensure(sizeof(double) * size_t(hist_cap) * B));
+    QCUDA(S, cudaMemsetAsync(S->hist_d.ptr, 0, sizeof(double) * size_t(hist_cap) * B, st_));
+    d_hist = S->hist_d.as<double>();
+  }
+  const bool want_debug = debug_traj && debug_cap > 0 && S->opt.populate_debug;
+  if (want_debug) {
+    QCUDA(S, S->debug_d.ensure(sizeof(double) * size_t(debug_cap) * N * 17 * B));
+    d_debug = S->debug_d.as<double>();
+  }
+  QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
+  rc = solve_core(S, B, N, S->desired_soa.as<double>(), Bd, S->traj_soa.as<double>(), d_k, d_K, d_hist, hist_cap,
+                  S->results_d.as<qilqr_result_t>(), d_debug, debug_cap);
+  if (rc) return rc;
+  // results back: stage_a still holds the input AoS (time_s column), unpack over it
+  unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
+  QCUDA(S, cudaMemcpyAsync(out_traj, S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+  if (results) QCUDA(S, cudaMemcpyAsync(results, S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost, st_));
+  if (out_k) {
+    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+    transpose_to_aos(S, d_k, S->stage_c.as<double>(), B, N, 4);
+    QCUDA(S, cudaMemcpyAsync(out_k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
+  }
+  if (out_K) {
+    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+    transpose_to_aos(S, d_K, S->stage_c.as<double>(), B, N, 48);
+    QCUDA(S, cudaMemcpyAsync(out_K, S->stage_c.ptr, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyDeviceToHost, st_));
+  }
+  if (d_hist) {  // [hist_cap][B] -> [B][hist_cap]
+    QCUDA(S, S->stage_b.ensure(sizeof(double) * size_t(hist_cap) * B));
+    transpose_to_aos(S, d_hist, S->stage_b.as<double>(), B, 1, hist_cap);
+    QCUDA(S, cudaMemcpyAsync(cost_hist, S->stage_b.ptr, sizeof(double) * size_t(hist_cap) * B, cudaMemcpyDeviceToHost, st_));
+  }
+  QCUDA(S, cudaStreamSynchronize(st_));
+  if (want_debug) {
+    // [cap][N][17][B] on the device -> [B][cap][N][18] on the host, one slot at a time
+    std::vector<qilqr_result_t> res(B);
+    QCUDA(S, cudaMemcpy(res.data(), S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost));
+    int max_nd = 0;
+    for (int b = 0; b < B; ++b) max_nd = std::max(max_nd, res[b].num_debug);
+    max_nd = std::min(max_nd, debug_cap);
+    std::vector<double> slot(size_t(B) * N * 18);
+    for (int sidx = 0; sidx < max_nd; ++sidx) {
+      // stage_a still has time_s in column 0
+      unpack_traj(S, B, N, d_debug + size_t(sidx) * N * 17 * B, S->stage_a.as<double>());
+      QCUDA(S, cudaMemcpyAsync(slot.data(), S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+      QCUDA(S, cudaStreamSynchronize(st_));
+      for (int b = 0; b < B; ++b)
+        if (sidx < res[b].num_debug)
+          std::memcpy(debug_traj + (size_t(b) * debug_cap + sidx) * N * 18, slot.data() + size_t(b) * N * 18,
+                      sizeof(double) * N * 18);
+    }
+  }
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_forward_sim_host(qilqr_solver_t *S, int B, int N, const double *current, const double *k, const double *K,
+                           const double *alpha, double *out_traj) {
+  if (!S || !current || !k || !K || !alpha || !out_traj || B <= 0 || N <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->stream;
+  QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->buf1.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B));
+  QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
+  QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+  QCUDA(S, S->misc.ensure(sizeof(double) * size_t(B)));
+  int rc = upload_traj(S, S->stage_a, B, N, current, S->traj_soa.as<double>());
+  if (rc) return rc;
+  QCUDA(S, cudaMemcpyAsync(S->stage_c.ptr, k, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyHostToDevice, st_));
+  transpose_to_soa(S, S->stage_c.as<double>(), S->gk.as<double>(), B, N, 4);
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaMemcpyAsync(S->stage_c.ptr, K, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyHostToDevice, st_));
+  transpose_to_soa(S, S->stage_c.as<double>(), S->gK.as<double>(), B, N, 48);
+  QCUDA(S, cudaMemcpyAsync(S->misc.ptr, alpha, sizeof(double) * size_t(B), cudaMemcpyHostToDevice, st_));
+  Problem pr{B, N, 1, nullptr, nullptr, nullptr, S->gk.as<double>(), S->gK.as<double>()};
+  RolloutArgs ra{pr, SolveState{}, nullptr, B, 0, MODE_FORWARD, S->traj_soa.as<double>(), S->buf1.as<double>(),
+                 S->misc.as<double>(), nullptr};
+  k_rollout<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, ra);
+  ++S->launches;
+  unpack_traj(S, B, N, S->buf1.as<double>(), S->stage_a.as<double>());
+  QCUDA(S, cudaMemcpyAsync(out_traj, S->stage_a.ptr, sizeof(double) * size_t(B) * N * 18, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_cost_trajectory_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, int n_desired,
+                               const double *traj, double *cost) {
+  if (!S || !desired || !traj || !cost || B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return QILQR_ERR_INVALID_ARGUMENT;
+  if (n_desired < N) return fail(S, QILQR_ERR_OUT_OF_RANGE, "vector::_M_range_check (cost.hh:39-40)");
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->stream;
+  QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(n_desired) * 17 * Bd));
+  QCUDA(S, S->misc.ensure(sizeof(double) * size_t(B)));
+  int rc = upload_traj(S, S->stage_b, Bd, n_desired, desired, S->desired_soa.as<double>());
+  if (rc) return rc;
+  rc = upload_traj(S, S->stage_a, B, N, traj, S->traj_soa.as<double>());
+  if (rc) return rc;
+  k_cost_trajectory<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, S->traj_soa.as<double>(), S->desired_soa.as<double>(),
+                                                         B, N, Bd, S->misc.as<double>());
+  ++S->launches;
+  QCUDA(S, cudaMemcpyAsync(cost, S->misc.ptr, sizeof(double) * size_t(B), cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_backwards_pass_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *traj,
+                              double *k, double *K, double *terms) {
+  if (!S || !desired || !traj || !k || !K || !terms || B <= 0 || N <= 0 || (Bd != 1 && Bd != B))
+    return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->stream;
+  QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(N) * 17 * Bd));
+  QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B));
+  QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
+  QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+  QCUDA(S, S->misc.ensure(sizeof(double) * 2 * size_t(B)));
+  int rc = upload_traj(S, S->stage_b, Bd, N, desired, S->desired_soa.as<double>());
+  if (rc) return rc;
+  rc = upload_traj(S, S->stage_a, B, N, traj, S->traj_soa.as<double>());
+  if (rc) return rc;
+  Problem pr{B, N, Bd, nullptr, nullptr, S->desired_soa.as<double>(), S->gk.as<double>(), S->gK.as<double>()};
+  BackwardArgs ba{pr, SolveState{}, nullptr, B, 0, 0, S->traj_soa.as<double>(), S->misc.as<double>()};
+  k_backward_t1<<<blocks_for(B, 64), 64, 0, st_>>>(S->p, ba);
+  ++S->launches;
+  transpose_to_aos(S, S->gk.as<double>(), S->stage_c.as<double>(), B, N, 4);
+  QCUDA(S, cudaMemcpyAsync(k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  transpose_to_aos(S, S->gK.as<double>(), S->stage_c.as<double>(), B, N, 48);
+  QCUDA(S, cudaMemcpyAsync(K, S->stage_c.ptr, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaMemcpyAsync(terms, S->misc.ptr, sizeof(double) * 2 * size_t(B), cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *current,
+                           const double *current_cost, const double *k, const double *K, const double *terms,
+                           double *out_traj, double *new_cost, double *step, int32_t *status) {
+  if (!S || !desired || !current || !current_cost || !k || !K || !terms || !out_traj || !new_cost || !step ||
+      !status || B <= 0 || N <= 0 || (Bd != 1 && Bd != B))
+    return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->stream;
+  int rc = ensure_state(S, B);
+  if (rc) return rc;
+  QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->buf1.ensure(sizeof(double) * size_t(N) * 17 * B));
+  QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(N) * 17 * Bd));
+  QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B));
+  QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
+  QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+  rc = upload_traj(S, S->stage_b, Bd, N, desired, S->desired_soa.as<double>());
+  if (rc) return rc;
+  rc = upload_traj(S, S->stage_a, B, N, current, S->traj_soa.as<double>());
+  if (rc) return rc;
+  QCUDA(S, cudaMemcpyAsync(S->stage_c.ptr, k, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyHostToDevice, st_));
+  transpose_to_soa(S, S->stage_c.as<double>(), S->gk.as<double>(), B, N, 4);
+  QCUDA(S, cudaStreamSynchronize(st_));
+  QCUDA(S, cudaMemcpyAsync(S->stage_c.ptr, K, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyHostToDevice, st_));
+  transpose_to_soa(S, S->stage_c.as<double>(), S->gK.as<double>(), B, N, 48);
+  Problem pr{B, N, Bd, S->traj_soa.as<double>(), S->buf1.as<double>(), S->desired_soa.as<double>(),
+             S->gk.as<double>(), S->gK.as<double>()};
+  SolveState st = make_state(S, B, nullptr, 0);
+  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B);
+  ++S->launches;
+  std::vector<double> q(B), kq(B);
+  for (int b = 0; b < B; ++b) { q[b] = terms[2 * b]; kq[b] = terms[2 * b + 1]; }
+  QCUDA(S, cudaMemcpyAsync(st.cost, current_cost, sizeof(double) * B, cudaMemcpyHostToDevice, st_));
+  QCUDA(S, cudaMemcpyAsync(st.qutk, q.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st_));
+  QCUDA(S, cudaMemcpyAsync(st.ktquuk, kq.data(), sizeof(double) * B, cudaMemcpyHostToDevice, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  int *listS[2] = {S->lists.as<int>(), S->lists.as<int>() + B};
+  int *dummy = S->lists.as<int>() + 2 * size_t(B);
+  const int *search = nullptr;
+  int n_search = B, s = 0;
+  while (n_search > 0) {
+    RolloutArgs ra{pr, st, search, n_search, 1, MODE_LINE_SEARCH, nullptr, nullptr, nullptr, nullptr};
+    k_rollout<<<blocks_for(n_search, 128), 128, 0, st_>>>(S->p, ra);
+    // phase: rejected problems keep PHASE_ACTIVE(0)... mark searching ones explicitly below
+    k_compact<<<1, 1024, 0, st_>>>(search, n_search, st.phase, dummy, listS[s], S->d_counts);
+    S->launches += 2;
+    QCUDA(S, cudaStreamSynchronize(st_));
+    n_search = S->h_counts[1];  // still PHASE_ACTIVE = not yet accepted and not failed
+    search = listS[s];
+    s = 1 - s;
+  }
+  dim3 grid(blocks_for(B, 128), 64);
+  k_collect<<<grid, 128, 0, st_>>>(pr, st.sel);
+  ++S->launches;
+  unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
+  QCUDA(S, cudaMemcpyAsync(out_traj, S->stage_a.ptr, sizeof(double) * size_t(B) * N * 18, cudaMemcpyDeviceToHost, st_));
+  std::vector<int> hstatus(B);
+  std::vector<double> halpha(B);
+  QCUDA(S, cudaMemcpyAsync(new_cost, st.cost, sizeof(double) * B, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaMemcpyAsync(halpha.data(), st.alpha, sizeof(double) * B, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaMemcpyAsync(hstatus.data(), st.status, sizeof(int) * B, cudaMemcpyDeviceToHost, st_));
+  QCUDA(S, cudaStreamSynchronize(st_));
+  for (int b = 0; b < B; ++b) {
+    status[b] = (hstatus[b] == QILQR_STATUS_LINE_SEARCH_FAILED) ? QILQR_ERR_LINE_SEARCH : QILQR_OK;
+    step[b] = halpha[b];
+  }
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+// ---- model / cost entry points (array-of-structs, one thread per problem) -----------
+namespace {
+struct Staged {
+  std::vector<void *> ptrs;
+  ~Staged() { for (void *p : ptrs) cudaFree(p); }
+  double *in(qilqr_solver *S, const double *h, size_t n, int &rc) {
+    if (!h) return nullptr;
+    void *d = nullptr;
+    if (cudaMalloc(&d, n * sizeof(double)) != cudaSuccess) { rc = QILQR_ERR_OUT_OF_MEMORY; return nullptr; }
+    ptrs.push_back(d);
+    if (cudaMemcpyAsync(d, h, n * sizeof(double), cudaMemcpyHostToDevice, S->stream) != cudaSuccess) rc = QILQR_ERR_CUDA;
+    return static_cast<double *>(d);
+  }
+  double *out(const double *h, size_t n, int &rc) {
+    if (!h) return nullptr;
+    void *d = nullptr;
+    if (cudaMalloc(&d, n * sizeof(double)) != cudaSuccess) { rc = QILQR_ERR_OUT_OF_MEMORY; return nullptr; }
+    ptrs.push_back(d);
+    return static_cast<double *>(d);
+  }
+};
+int fetch(qilqr_solver *S, double *h, const double *d, size_t n) {
+  if (!h) return QILQR_OK;
+  QCUDA(S, cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, S->stream));
+  return QILQR_OK;
+}
+}  // namespace
+
+int qilqr_discrete_dynamics_host(qilqr_solver_t *S, int B, const double *x, const double *u, double *x_next,
+                                 double *J_x, double *J_u) {
+  if (!S || !x || !u || !x_next || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = 0;
+  Staged sg;
+  double *dx = sg.in(S, x, size_t(B) * 13, rc), *du = sg.in(S, u, size_t(B) * 4, rc);
+  double *dn = sg.out(x_next, size_t(B) * 13, rc), *dJx = sg.out(J_x, size_t(B) * 144, rc), *dJu = sg.out(J_u, size_t(B) * 48, rc);
+  if (rc) return rc;
+  k_api_discrete_dynamics<<<blocks_for(B, 64), 64, 0, S->stream>>>(S->p, B, dx, du, dn, dJx, dJu);
+  ++S->launches;
+  if ((rc = fetch(S, x_next, dn, size_t(B) * 13)) || (rc = fetch(S, J_x, dJx, size_t(B) * 144)) ||
+      (rc = fetch(S, J_u, dJu, size_t(B) * 48)))
+    return rc;
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_continuous_dynamics_host(qilqr_solver_t *S, int B, const double *x, const double *u, double *xdot,
+                                   double *J_x, double *J_u) {
+  if (!S || !x || !u || !xdot || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = 0;
+  Staged sg;
+  double *dx = sg.in(S, x, size_t(B) * 13, rc), *du = sg.in(S, u, size_t(B) * 4, rc);
+  double *dd = sg.out(xdot, size_t(B) * 12, rc), *dJx = sg.out(J_x, size_t(B) * 144, rc), *dJu = sg.out(J_u, size_t(B) * 48, rc);
+  if (rc) return rc;
+  k_api_continuous_dynamics<<<blocks_for(B, 64), 64, 0, S->stream>>>(S->p, B, dx, du, dd, dJx, dJu);
+  ++S->launches;
+  if ((rc = fetch(S, xdot, dd, size_t(B) * 12)) || (rc = fetch(S, J_x, dJx, size_t(B) * 144)) ||
+      (rc = fetch(S, J_u, dJu, size_t(B) * 48)))
+    return rc;
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_state_minus_host(qilqr_solver_t *S, int B, const double *lhs, const double *rhs, double *out, double *J_lhs,
+                           double *J_rhs) {
+  if (!S || !lhs || !rhs || !out || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = 0;
+  Staged sg;
+  double *dl = sg.in(S, lhs, size_t(B) * 13, rc), *dr = sg.in(S, rhs, size_t(B) * 13, rc);
+  double *dout = sg.out(out, size_t(B) * 12, rc), *dJl = sg.out(J_lhs, size_t(B) * 144, rc), *dJr = sg.out(J_rhs, size_t(B) * 144, rc);
+  if (rc) return rc;
+  k_api_state_minus<<<blocks_for(B, 64), 64, 0, S->stream>>>(B, dl, dr, dout, dJl, dJr);
+  ++S->launches;
+  if ((rc = fetch(S, out, dout, size_t(B) * 12)) || (rc = fetch(S, J_lhs, dJl, size_t(B) * 144)) ||
+      (rc = fetch(S, J_rhs, dJr, size_t(B) * 144)))
+    return rc;
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_state_add_host(qilqr_solver_t *S, int B, const double *x, const double *tangent, double *out, double *J_lhs,
+                         double *J_rhs) {
+  if (!S || !x || !tangent || !out || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = 0;
+  Staged sg;
+  double *dx = sg.in(S, x, size_t(B) * 13, rc), *dt = sg.in(S, tangent, size_t(B) * 12, rc);
+  double *dout = sg.out(out, size_t(B) * 13, rc), *dJl = sg.out(J_lhs, size_t(B) * 144, rc), *dJr = sg.out(J_rhs, size_t(B) * 144, rc);
+  if (rc) return rc;
+  k_api_state_add<<<blocks_for(B, 64), 64, 0, S->stream>>>(B, dx, dt, dout, dJl, dJr);
+  ++S->launches;
+  if ((rc = fetch(S, out, dout, size_t(B) * 13)) || (rc = fetch(S, J_lhs, dJl, size_t(B) * 144)) ||
+      (rc = fetch(S, J_rhs, dJr, size_t(B) * 144)))
+    return rc;
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_cost_host(qilqr_solver_t *S, int B, const double *x, const double *u, const double *x_d, const double *u_d,
+                    double *cost, double *C_x, double *C_u, double *C_xx, double *C_uu, double *C_xu) {
+  if (!S || !x || !u || !x_d || !u_d || !cost || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  int rc = 0;
+  Staged sg;
+  double *dx = sg.in(S, x, size_t(B) * 13, rc), *du = sg.in(S, u, size_t(B) * 4, rc);
+  double *dxd = sg.in(S, x_d, size_t(B) * 13, rc), *dud = sg.in(S, u_d, size_t(B) * 4, rc);
+  double *dc = sg.out(cost, size_t(B), rc), *dCx = sg.out(C_x, size_t(B) * 12, rc), *dCu = sg.out(C_u, size_t(B) * 4, rc);
+  double *dCxx = sg.out(C_xx, size_t(B) * 144, rc), *dCuu = sg.out(C_uu, size_t(B) * 16, rc), *dCxu = sg.out(C_xu, size_t(B) * 48, rc);
+  if (rc) return rc;
+  k_api_cost<<<blocks_for(B, 64), 64, 0, S->stream>>>(S->p, B, dx, du, dxd, dud, dc, dCx, dCu, dCxx, dCuu, dCxu);
+  ++S->launches;
+  if ((rc = fetch(S, cost, dc, size_t(B))) || (rc = fetch(S, C_x, dCx, size_t(B) * 12)) ||
+      (rc = fetch(S, C_u, dCu, size_t(B) * 4)) || (rc = fetch(S, C_xx, dCxx, size_t(B) * 144)) ||
+      (rc = fetch(S, C_uu, dCuu, size_t(B) * 16)) || (rc = fetch(S, C_xu, dCxu, size_t(B) * 48)))
+    return rc;
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = double(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace
+
+int qilqr_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return QILQR_ERR_INVALID_ARGUMENT;
+  if (cudaSetDevice(device) != cudaSuccess) return QILQR_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return QILQR_ERR_NO_DEVICE;
+  double *d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
+    if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return cudaGetLastError() == cudaSuccess ? QILQR_OK : QILQR_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,788 @@
+// =============================================================================
+// qilqr_kernels.cuh -- CUDA kernels of the batched iLQR hot path (sm_100a).
+//
+// Data layout in HBM (structure of arrays, problem index fastest so that a warp
+// of 32 problems reads 256 contiguous bytes per row):
+//   trajectory  double[N][17][B]   rows 0-2 t, 3-6 q(x,y,z,w), 7-12 body velocity, 13-16 control
+//   desired     double[N][17][Bd]  Bd = 1 (shared) or B
+//   k           double[N][4][B]
+//   K           double[N][48][B]   row = 12*control + state   (ILQR::FeedbackGains, ilqr.hh:40-41)
+// Each problem has two trajectory buffers; `sel[b]` says which one is current, so
+// accepting a line-search candidate is a bit flip, not a copy.
+//
+// Kernels
+//   k_cost_trajectory   ILQR::cost_trajectory      (ilqr.hh:89-95)
+//   k_backward          ILQR::backwards_pass       (ilqr.hh:97-147) + exit A of solve (:61-68)
+//   k_rollout           ILQR::forward_sim + cost   (ilqr.hh:149-172, 89-95) + Armijo test of
+//                       line_search (:182-189) + exit B of solve (:78-84)
+//   k_compact           ordered stream compaction of the active / searching problem lists
+// =============================================================================
+#pragma once
+#include "qilqr_device.cuh"
+#include "../../include/qilqr.h"
+
+namespace qilqr {
+
+enum Phase : int { PHASE_ACTIVE = 0, PHASE_SEARCH = 1, PHASE_DONE = 2 };
+enum RolloutMode : int { MODE_FORWARD = 0, MODE_SOLVE = 1, MODE_LINE_SEARCH = 2 };
+
+struct Problem {
+  int B;   // batch (also the pitch of every SoA row)
+  int N;   // knots
+  int Bd;  // desired_count: 1 or B
+  double *buf0, *buf1;    // trajectory double-buffer
+  const double *desired;  // [N][17][Bd]
+  double *gk, *gK;        // gains
+};
+
+struct SolveState {  // one entry per problem
+  double *cost;      // actual cost of the current trajectory ("cost"/"new_cost" in ilqr.hh:56-75)
+  double *new_cost;  // cost of the last candidate
+  double *qutk, *ktquuk;  // detail::CostReductionTerms (ilqr.hh:13-16)
+  double *alpha;
+  int *ls_iter, *status, *bwd, *rollouts, *ndebug, *sel, *phase, *accepted_iter;
+  double *cost_hist;  // [hist_cap][B] or nullptr
+  int hist_cap;
+};
+
+QD size_t row_index(int i, int c, int rows, int B, int b) { return (size_t(i) * rows + c) * size_t(B) + b; }
+
+QD void load_point(const double *traj, int i, int B, int b, double *x /*13*/, double *u /*4*/) {
+#pragma unroll
+  for (int c = 0; c < 13; ++c) x[c] = traj[row_index(i, c, 17, B, b)];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) u[c] = traj[row_index(i, 13 + c, 17, B, b)];
+}
+QD void store_point(double *traj, int i, int B, int b, const double *x, const double *u) {
+#pragma unroll
+  for (int c = 0; c < 13; ++c) traj[row_index(i, c, 17, B, b)] = x[c];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) traj[row_index(i, 13 + c, 17, B, b)] = u[c];
+}
+
+// ILQR::is_converged (ilqr.hh:196-205)
+QD bool is_converged(const DeviceParams &p, double cost, double new_cost) {
+  const double d = fabs(cost - new_cost);
+  if (d / fabs(cost) < p.rtol) return true;
+  if (d < p.atol) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------------------
+// cost_trajectory
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_cost_trajectory(const __grid_constant__ DeviceParams p, const double *traj, const double *desired,
+                  int B, int N, int Bd, double *cost_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int bd = (Bd == 1) ? 0 : b;
+  double cost = 0.0;
+  for (int i = 0; i < N; ++i) {
+    double x[13], u[4], xd[13], ud[4], dx[12], du[4];
+    load_point(traj, i, B, b, x, u);
+    load_point(desired, i, Bd, bd, xd, ud);
+    state_minus(x, xd, dx, nullptr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) du[j] = u[j] - ud[j];
+    cost = cost + quadratic_cost(p, dx, du);
+  }
+  cost_out[b] = cost;
+}
+
+// ---------------------------------------------------------------------------
+// forward_sim + cost_trajectory (+ line-search bookkeeping), one thread per problem
+// ---------------------------------------------------------------------------
+struct RolloutArgs {
+  Problem pr;
+  SolveState st;
+  const int *list;  // problems to roll out (nullptr: 0..n-1)
+  int n;
+  int iter;  // outer iteration index i of solve()
+  int mode;  // RolloutMode
+  // MODE_FORWARD only: explicit buffers and step sizes
+  const double *cur;
+  double *out;
+  const double *alpha_in;
+  double *cost_out;  // may be nullptr
+};
+
+__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n) return;
+  const int b = a.list ? a.list[t] : t;
+  const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
+  const int bd = (Bd == 1) ? 0 : b;
+  const double *cur;
+  double *cand;
+  double alpha;
+  if (a.mode == MODE_FORWARD) {
+    cur = a.cur; cand = a.out; alpha = a.alpha_in[b];
+  } else {
+    const int s = a.st.sel[b];
+    cur = s ? a.pr.buf1 : a.pr.buf0;
+    cand = s ? a.pr.buf0 : a.pr.buf1;
+    alpha = a.st.alpha[b];
+  }
+  const bool want_cost = (a.mode != MODE_FORWARD) || (a.cost_out != nullptr);
+
+  double x[13], ubar[4];
+  load_point(cur, 0, B, b, x, ubar);  // state = current_traj.front().state (ilqr.hh:156)
+  double cost = 0.0;
+  for (int i = 0; i < N; ++i) {
+    double xbar[13];
+    load_point(cur, i, B, b, xbar, ubar);
+    double d[12];
+    state_minus(x, xbar, d, nullptr);  // (state - current_traj[i].state).coeffs()
+    double u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double kj = a.pr.gk[row_index(i, j, 4, B, b)];
+      double Kd = a.pr.gK[row_index(i, 12 * j, 48, B, b)] * d[0];
+#pragma unroll
+      for (int s = 1; s < 12; ++s) Kd = fma(a.pr.gK[row_index(i, 12 * j + s, 48, B, b)], d[s], Kd);
+      u[j] = (ubar[j] + alpha * kj) + Kd;
+    }
+    store_point(cand, i, B, b, x, u);
+    if (want_cost) {
+      double xd[13], ud[4], dx[12], du[4];
+      load_point(a.pr.desired, i, Bd, bd, xd, ud);
+      state_minus(x, xd, dx, nullptr);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) du[j] = u[j] - ud[j];
+      cost = cost + quadratic_cost(p, dx, du);
+    }
+    discrete_step(p, x, x + 3, x + 7, u);  // also after the last knot, as ilqr.hh:168 does; result unused
+  }
+
+  if (a.mode == MODE_FORWARD) {
+    if (a.cost_out) a.cost_out[b] = cost;
+    return;
+  }
+  // ---- line_search / solve bookkeeping ----
+  const SolveState &st = a.st;
+  st.rollouts[b] += 1;
+  st.new_cost[b] = cost;
+  const double cur_cost = st.cost[b];
+  bool accept;
+  if (a.mode == MODE_SOLVE && a.iter == 0) {
+    accept = true;  // ilqr.hh:70-73: no acceptance test on the first iteration
+  } else {
+    const double desired = p.desired_reduction_frac * (alpha * st.qutk[b] + alpha * alpha * st.ktquuk[b] / 2.0);
+    accept = (cost - cur_cost < desired);  // ilqr.hh:186; NaN -> reject
+  }
+  if (accept) {
+    st.sel[b] ^= 1;
+    st.cost[b] = cost;
+    st.accepted_iter[b] = a.iter;
+    const int nd = st.ndebug[b];
+    if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
+    st.ndebug[b] = nd + 1;
+    if (a.mode == MODE_SOLVE && a.iter > 0 && is_converged(p, cur_cost, cost)) {
+      st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
+      st.phase[b] = PHASE_DONE;
+    } else if (a.mode == MODE_LINE_SEARCH) {
+      st.phase[b] = PHASE_DONE;
+    } else {
+      st.phase[b] = PHASE_ACTIVE;
+    }
+  } else {
+    st.alpha[b] = alpha * p.step_update;  // ilqr.hh:189
+    const int ls = st.ls_iter[b] + 1;
+    st.ls_iter[b] = ls;
+    if (ls >= p.ls_max_iters) {
+      st.status[b] = QILQR_STATUS_LINE_SEARCH_FAILED;  // ilqr.hh:191-193
+      st.phase[b] = PHASE_DONE;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Eigen::LDLT<Matrix4d> semantics (pivot on the largest remaining |diagonal|,
+// lower triangle only, D pseudo-inverse) -- ilqr.hh:126-128.  m: row-major 4x4.
+// ---------------------------------------------------------------------------
+struct Ldlt4 {
+  double m[16];
+  int tr[4];
+};
+QD void ldlt4_compute(Ldlt4 &f) {
+  double *m = f.m;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int piv = k;
+    double best = fabs(m[5 * k]);
+#pragma unroll
+    for (int i = k + 1; i < 4; ++i) {
+      const double v = fabs(m[5 * i]);
+      if (v > best) { best = v; piv = i; }
+    }
+    f.tr[k] = piv;
+    if (piv != k) {
+      for (int j = 0; j < k; ++j) { const double t = m[4 * k + j]; m[4 * k + j] = m[4 * piv + j]; m[4 * piv + j] = t; }
+      for (int i = piv + 1; i < 4; ++i) { const double t = m[4 * i + k]; m[4 * i + k] = m[4 * i + piv]; m[4 * i + piv] = t; }
+      { const double t = m[5 * k]; m[5 * k] = m[5 * piv]; m[5 * piv] = t; }
+      for (int i = k + 1; i < piv; ++i) { const double t = m[4 * i + k]; m[4 * i + k] = m[4 * piv + i]; m[4 * piv + i] = t; }
+    }
+    if (k > 0) {
+      double temp[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) if (j < k) temp[j] = m[5 * j] * m[4 * k + j];
+      double acc = m[4 * k] * temp[0];
+#pragma unroll
+      for (int j = 1; j < 3; ++j) if (j < k) acc = fma(m[4 * k + j], temp[j], acc);
+      m[5 * k] = m[5 * k] - acc;
+#pragma unroll
+      for (int i = k + 1; i < 4; ++i) {
+        double a2 = m[4 * i] * temp[0];
+#pragma unroll
+        for (int j = 1; j < 3; ++j) if (j < k) a2 = fma(m[4 * i + j], temp[j], a2);
+        m[4 * i + k] = m[4 * i + k] - a2;
+      }
+    }
+    const double akk = m[5 * k];
+    const bool valid = fabs(akk) > 0.0;
+    if (k == 0 && !valid) {
+      f.tr[0] = 0; f.tr[1] = 1; f.tr[2] = 2; f.tr[3] = 3;
+      return;
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = k + 1; i < 4; ++i) m[4 * i + k] = m[4 * i + k] / akk;
+    }
+  }
+}
+QD void ldlt4_solve(const Ldlt4 &f, double *x /*4, in place*/) {
+  const double *m = f.m;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int t = f.tr[k];
+    if (t != k) { const double s = x[k]; x[k] = x[t]; x[t] = s; }
+  }
+  x[1] = x[1] - m[4] * x[0];
+  x[2] = x[2] - m[8] * x[0] - m[9] * x[1];
+  x[3] = x[3] - m[12] * x[0] - m[13] * x[1] - m[14] * x[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = (fabs(m[5 * i]) > 2.2250738585072014e-308) ? x[i] / m[5 * i] : 0.0;
+  x[2] = x[2] - m[14] * x[3];
+  x[1] = x[1] - m[9] * x[2] - m[13] * x[3];
+  x[0] = x[0] - m[4] * x[1] - m[8] * x[2] - m[12] * x[3];
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    const int t = f.tr[k];
+    if (t != k) { const double s = x[k]; x[k] = x[t]; x[t] = s; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// backwards_pass, one thread per problem ("T1").  12x12 matrices are stored as
+// 4x4 grids of 3x3 blocks: block (I,J) at X + (4*I+J)*9.
+// ---------------------------------------------------------------------------
+#define QBLK(X, I, J) ((X) + (4 * (I) + (J)) * 9)
+QD double &bel(double *X, int r, int c) { return X[(4 * (r / 3) + (c / 3)) * 9 + 3 * (r % 3) + (c % 3)]; }
+
+struct BackwardArgs {
+  Problem pr;
+  SolveState st;
+  const int *list;
+  int n;
+  int iter;
+  int solve_mode;       // 1: solve() bookkeeping (exit A); 0: plain backwards_pass
+  const double *traj;   // solve_mode == 0 only
+  double *terms_out;    // solve_mode == 0 only: [B][2]
+};
+
+// Cost derivatives at one knot (cost.hh:47-57) in block form.
+//   J = blkdiag([[Ji, Qi], [0, Ji]], I6);  C.x = ((2 dx^T) Q) J;  C.xx = ((2 J^T) Q) J
+QD void cost_derivatives(const DeviceParams &p, const double *dx, const double *Ji, const double *Qi,
+                         double *Cx /*12*/, double *Cxx /*block-major 144*/) {
+  // y = (2 dx)^T Q
+  double y[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    double s = (2.0 * dx[0]) * p.Q[j];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+    y[j] = s;
+  }
+  m3T_vec(Ji, y, Cx);
+  m3T_vec(Qi, y, Cx + 3);
+  m3T_vec_add(Ji, y + 3, Cx + 3);
+#pragma unroll
+  for (int j = 6; j < 12; ++j) Cx[j] = y[j];
+  // P = (2 J^T) Q, row-major dense 12x12
+  double P[144];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      // row i (<3): sum_k 2*Ji[k][i] Q[k][j]
+      P[12 * i + j] = fma(2.0 * Ji[6 + i], p.Q[24 + j], fma(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
+      // row 3+i: sum_k 2*Qi[k][i] Q[k][j] + sum_k 2*Ji[k][i] Q[3+k][j]
+      double s = fma(2.0 * Qi[6 + i], p.Q[24 + j], fma(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
+      s = fma(2.0 * Ji[i], p.Q[36 + j], s);
+      s = fma(2.0 * Ji[3 + i], p.Q[48 + j], s);
+      s = fma(2.0 * Ji[6 + i], p.Q[60 + j], s);
+      P[12 * (3 + i) + j] = s;
+    }
+#pragma unroll
+    for (int i = 6; i < 12; ++i) P[12 * i + j] = 2.0 * p.Q[12 * i + j];
+  }
+  // Cxx = P J
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      bel(Cxx, i, j) = fma(P[12 * i + 2], Ji[6 + j], fma(P[12 * i + 1], Ji[3 + j], P[12 * i] * Ji[j]));
+      double s = fma(P[12 * i + 2], Qi[6 + j], fma(P[12 * i + 1], Qi[3 + j], P[12 * i] * Qi[j]));
+      s = fma(P[12 * i + 3], Ji[j], s);
+      s = fma(P[12 * i + 4], Ji[3 + j], s);
+      s = fma(P[12 * i + 5], Ji[6 + j], s);
+      bel(Cxx, i, 3 + j) = s;
+    }
+#pragma unroll
+    for (int j = 6; j < 12; ++j) bel(Cxx, i, j) = P[12 * i + j];
+  }
+}
+
+__global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ DeviceParams p, const __grid_constant__ BackwardArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n) return;
+  const int b = a.list ? a.list[t] : t;
+  const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
+  const int bd = (Bd == 1) ? 0 : b;
+  const double *traj = a.solve_mode ? (a.st.sel[b] ? a.pr.buf1 : a.pr.buf0) : a.traj;
+
+  double V[144], vx[12];
+#pragma unroll
+  for (int i = 0; i < 144; ++i) V[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) vx[i] = 0.0;
+  double QuTk = 0.0, kTQuuk = 0.0;
+
+  for (int i = N - 1; i >= 0; --i) {
+    double x[13], u[4], xd[13], ud[4];
+    load_point(traj, i, B, b, x, u);
+    load_point(a.pr.desired, i, Bd, bd, xd, ud);
+
+    ABlocks A;
+    dynamics_blocks(p, x + 3, x + 7, A);
+
+    double dx[12], Jli[9], Ji[9], Qi[9];
+    state_minus(x, xd, dx, Jli);
+    se3_rjacinv_blocks(dx, Jli, Ji, Qi);
+    double Cx[12], Qxx[144];
+    cost_derivatives(p, dx, Ji, Qi, Cx, Qxx);  // Qxx starts as C.xx
+    double Cu[4];
+    {
+      double du[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) du[j] = u[j] - ud[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double s = (2.0 * du[0]) * p.R[j];
+#pragma unroll
+        for (int l = 1; l < 4; ++l) s = fma(2.0 * du[l], p.R[4 * l + j], s);
+        Cu[j] = s;
+      }
+    }
+
+    // M = A^T V   (J_x^T v_xx, ilqr.hh:121,123)
+    double M[144];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      m3_mulT(A.Re, QBLK(V, 0, c), QBLK(M, 0, c));
+      m3_mulT(A.Te, QBLK(V, 0, c), QBLK(M, 1, c));
+      m3_maddT(A.Re, QBLK(V, 1, c), QBLK(M, 1, c));
+      m3_maddT(A.dG, QBLK(V, 2, c), QBLK(M, 1, c));
+      m3_mulT(A.dJr, QBLK(V, 0, c), QBLK(M, 2, c));
+#pragma unroll
+      for (int e = 0; e < 9; ++e) QBLK(M, 2, c)[e] += QBLK(V, 2, c)[e];
+      m3_mulT(A.dQb, QBLK(V, 0, c), QBLK(M, 3, c));
+      m3_maddT(A.dJr, QBLK(V, 1, c), QBLK(M, 3, c));
+      m3_maddT(A.Wd, QBLK(V, 3, c), QBLK(M, 3, c));
+    }
+    // Q.xx = C.xx + M A
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double T[9];
+      m3_mul(QBLK(M, r, 0), A.Re, T);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) QBLK(Qxx, r, 0)[e] += T[e];
+      m3_mul(QBLK(M, r, 0), A.Te, T);
+      m3_madd(QBLK(M, r, 1), A.Re, T);
+      m3_madd(QBLK(M, r, 2), A.dG, T);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) QBLK(Qxx, r, 1)[e] += T[e];
+      m3_mul(QBLK(M, r, 0), A.dJr, T);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) QBLK(Qxx, r, 2)[e] += T[e] + QBLK(M, r, 2)[e];
+      m3_mul(QBLK(M, r, 0), A.dQb, T);
+      m3_madd(QBLK(M, r, 1), A.dJr, T);
+      m3_madd(QBLK(M, r, 3), A.Wd, T);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) QBLK(Qxx, r, 3)[e] += T[e];
+    }
+    // Q.xu = M B (C.xu = 0);  B rows 8..11 = p.Bu
+    double Qxu[48];
+#pragma unroll
+    for (int s = 0; s < 12; ++s)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double acc = bel(M, s, 8) * p.Bu[j];
+#pragma unroll
+        for (int c = 1; c < 4; ++c) acc = fma(bel(M, s, 8 + c), p.Bu[4 * c + j], acc);
+        Qxu[4 * s + j] = acc;
+      }
+    // Q.uu = C.uu + (B^T V) B
+    Ldlt4 f;
+    double Quu[16];
+    {
+      double BtV[16];  // only columns 8..11 of B^T V are needed
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double acc = p.Bu[j] * bel(V, 8, 8 + c);
+#pragma unroll
+          for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + j], bel(V, 8 + r, 8 + c), acc);
+          BtV[4 * j + c] = acc;
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          double acc = BtV[4 * j] * p.Bu[l];
+#pragma unroll
+          for (int c = 1; c < 4; ++c) acc = fma(BtV[4 * j + c], p.Bu[4 * c + l], acc);
+          Quu[4 * j + l] = 2.0 * p.R[4 * j + l] + acc;
+        }
+      if (p.quu_reg != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Quu[5 * j] += p.quu_reg;
+      }
+    }
+    // Q.x = C.x + A^T v_x ;  Q.u = C.u + B^T v_x
+    double Qx[12], Qu[4];
+    {
+      double T[12];
+      m3T_vec(A.Re, vx, T);
+      m3T_vec(A.Te, vx, T + 3);
+      m3T_vec_add(A.Re, vx + 3, T + 3);
+      m3T_vec_add(A.dG, vx + 6, T + 3);
+      m3T_vec(A.dJr, vx, T + 6);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) T[6 + e] += vx[6 + e];
+      m3T_vec(A.dQb, vx, T + 9);
+      m3T_vec_add(A.dJr, vx + 3, T + 9);
+      m3T_vec_add(A.Wd, vx + 9, T + 9);
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Qx[e] = Cx[e] + T[e];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double acc = p.Bu[j] * vx[8];
+#pragma unroll
+        for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + j], vx[8 + r], acc);
+        Qu[j] = Cu[j] + acc;
+      }
+    }
+    // gains: K = -Quu^-1 Qxu^T, k = -Quu^-1 Qu   (ilqr.hh:126-130)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f.m[e] = Quu[e];
+    ldlt4_compute(f);
+    double K[48], k[4];
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+      double rhs[4] = {Qxu[4 * s], Qxu[4 * s + 1], Qxu[4 * s + 2], Qxu[4 * s + 3]};
+      ldlt4_solve(f, rhs);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) K[12 * j + s] = -rhs[j];
+    }
+    {
+      double rhs[4] = {Qu[0], Qu[1], Qu[2], Qu[3]};
+      ldlt4_solve(f, rhs);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = -rhs[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a.pr.gk[row_index(i, j, 4, B, b)] = k[j];
+#pragma unroll
+    for (int e = 0; e < 48; ++e) a.pr.gK[row_index(i, e, 48, B, b)] = K[e];
+
+    // v_x = Q.x - (K^T Q.uu) k ; v_xx = Q.xx - (K^T Q.uu) K   (ilqr.hh:132-133)
+    double KtQ[48];  // [s][l]
+#pragma unroll
+    for (int s = 0; s < 12; ++s)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        double acc = K[s] * Quu[l];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) acc = fma(K[12 * j + s], Quu[4 * j + l], acc);
+        KtQ[4 * s + l] = acc;
+      }
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+      double acc = KtQ[4 * s] * k[0];
+#pragma unroll
+      for (int l = 1; l < 4; ++l) acc = fma(KtQ[4 * s + l], k[l], acc);
+      vx[s] = Qx[s] - acc;
+    }
+#pragma unroll
+    for (int s = 0; s < 12; ++s)
+#pragma unroll
+      for (int c = 0; c < 12; ++c) {
+        double acc = KtQ[4 * s] * K[c];
+#pragma unroll
+        for (int l = 1; l < 4; ++l) acc = fma(KtQ[4 * s + l], K[12 * l + c], acc);
+        bel(V, s, c) = bel(Qxx, s, c) - acc;
+      }
+    if (p.symmetrize_vxx) {
+#pragma unroll
+      for (int s = 0; s < 12; ++s)
+#pragma unroll
+        for (int c = s + 1; c < 12; ++c) {
+          const double m = 0.5 * (bel(V, s, c) + bel(V, c, s));
+          bel(V, s, c) = m;
+          bel(V, c, s) = m;
+        }
+#pragma unroll
+      for (int s = 0; s < 12; ++s) bel(V, s, s) = 0.5 * (bel(V, s, s) + bel(V, s, s));
+    }
+    // expected cost reduction terms (ilqr.hh:136-140)
+    {
+      double acc = Qu[0] * k[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j) acc = fma(Qu[j], k[j], acc);
+      QuTk = QuTk + acc;
+      double z[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        double s = k[0] * Quu[l];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) s = fma(k[j], Quu[4 * j + l], s);
+        z[l] = s;
+      }
+      double acc2 = z[0] * k[0];
+#pragma unroll
+      for (int l = 1; l < 4; ++l) acc2 = fma(z[l], k[l], acc2);
+      kTQuuk = kTQuuk + acc2;
+    }
+  }
+
+  if (!a.solve_mode) {
+    a.terms_out[2 * size_t(b)] = QuTk;
+    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
+    return;
+  }
+  const SolveState &st = a.st;
+  st.qutk[b] = QuTk;
+  st.ktquuk[b] = kTQuuk;
+  st.bwd[b] += 1;
+  const double cost = st.cost[b];
+  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
+  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
+    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
+    st.phase[b] = PHASE_DONE;
+  } else {
+    st.alpha[b] = 1.0;
+    st.ls_iter[b] = 0;
+    st.phase[b] = PHASE_SEARCH;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Ordered compaction of a problem list by phase (single block; the lists are
+// at most a few 10^4 entries and this runs twice per solver iteration).
+//   out_search <- entries with phase == SEARCH,  out_active <- phase == ACTIVE
+//   counts[0] = |out_search|, counts[1] = |out_active|   (mapped pinned host memory)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, const int *phase, int *out_search,
+                                                 int *out_active, volatile int *counts) {
+  __shared__ int warp_s[32], warp_a[32];
+  __shared__ int base_s, base_a;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { base_s = 0; base_a = 0; }
+  __syncthreads();
+  for (int start = 0; start < n_in; start += 1024) {
+    const int idx = start + tid;
+    int b = -1, ph = -1;
+    if (idx < n_in) {
+      b = list_in ? list_in[idx] : idx;
+      ph = phase[b];
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, ph == PHASE_SEARCH);
+    const unsigned ma = __ballot_sync(0xffffffffu, ph == PHASE_ACTIVE);
+    if (lane == 0) { warp_s[wid] = __popc(ms); warp_a[wid] = __popc(ma); }
+    __syncthreads();
+    if (wid == 0) {
+      int vs = warp_s[lane], va = warp_a[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ts = __shfl_up_sync(0xffffffffu, vs, o), ta = __shfl_up_sync(0xffffffffu, va, o);
+        if (lane >= o) { vs += ts; va += ta; }
+      }
+      warp_s[lane] = vs;  // inclusive
+      warp_a[lane] = va;
+    }
+    __syncthreads();
+    const int off_s = base_s + (wid ? warp_s[wid - 1] : 0) + __popc(ms & ((1u << lane) - 1));
+    const int off_a = base_a + (wid ? warp_a[wid - 1] : 0) + __popc(ma & ((1u << lane) - 1));
+    if (ph == PHASE_SEARCH) out_search[off_s] = b;
+    if (ph == PHASE_ACTIVE) out_active[off_a] = b;
+    __syncthreads();
+    if (tid == 0) { base_s += warp_s[31]; base_a += warp_a[31]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counts[0] = base_s;
+    counts[1] = base_a;
+    __threadfence_system();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Solve set-up / tear-down
+// ---------------------------------------------------------------------------
+__global__ void k_init_state(SolveState st, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  st.new_cost[b] = 0.0; st.qutk[b] = 0.0; st.ktquuk[b] = 0.0; st.alpha[b] = 1.0;
+  st.ls_iter[b] = 0; st.status[b] = QILQR_STATUS_NOT_RUN; st.bwd[b] = 0; st.rollouts[b] = 0;
+  st.ndebug[b] = 0; st.sel[b] = 0; st.phase[b] = PHASE_ACTIVE; st.accepted_iter[b] = -1;
+}
+// Problems still running after the loop bound hit max_iters (ilqr.hh:58,86); writes results.
+__global__ void k_finalize(SolveState st, int B, qilqr_result_t *res) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int s = st.status[b];
+  if (s == QILQR_STATUS_NOT_RUN) { s = QILQR_STATUS_MAX_ITERS; st.status[b] = s; }
+  if (res) {
+    res[b].status = s;
+    res[b].backward_passes = st.bwd[b];
+    res[b].rollouts = st.rollouts[b];
+    res[b].num_debug = st.ndebug[b];
+    res[b].final_cost = st.cost[b];
+  }
+}
+// Copy the current trajectory of the problems whose result sits in buf1 back to buf0.
+__global__ void k_collect(Problem pr, const int *sel) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pr.B || !sel[b]) return;
+  const int rows = pr.N * 17;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) pr.buf0[size_t(r) * pr.B + b] = pr.buf1[size_t(r) * pr.B + b];
+}
+// ILQRDebug capture (ilqr.hh:78-80): copy the trajectory accepted in iteration `iter`.
+__global__ void k_debug_capture(Problem pr, SolveState st, const int *list, int n, int iter, double *debug /*[cap][N*17][B]*/, int cap) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int b = list ? list[t] : t;
+  if (st.accepted_iter[b] != iter) return;
+  const int slot = st.ndebug[b] - 1;
+  if (slot < 0 || slot >= cap) return;
+  const double *src = st.sel[b] ? pr.buf1 : pr.buf0;
+  const int rows = pr.N * 17;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y)
+    debug[(size_t(slot) * rows + r) * pr.B + b] = src[size_t(r) * pr.B + b];
+}
+
+// ---------------------------------------------------------------------------
+// AoS [B][N][18] <-> SoA [N][17][B] transposition through shared memory.
+// Block: 32 problems x 18 components; grid.x = ceil(B/32), grid.y strides over knots.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(576) k_pack(const double *aos, double *soa, int B, int N) {
+  __shared__ double tile[18][33];
+  const int b0 = blockIdx.x * 32, tid = threadIdx.x;
+  for (int i = blockIdx.y; i < N; i += gridDim.y) {
+    {
+      const int c = tid % 18, bl = tid / 18;
+      if (b0 + bl < B) tile[c][bl] = aos[(size_t(b0 + bl) * N + i) * 18 + c];
+    }
+    __syncthreads();
+    {
+      const int bl = tid % 32, c = tid / 32;
+      if (c >= 1 && b0 + bl < B) soa[(size_t(i) * 17 + (c - 1)) * B + b0 + bl] = tile[c][bl];
+    }
+    __syncthreads();
+  }
+}
+// Leaves column 0 (time_s) of the AoS buffer untouched.
+__global__ void __launch_bounds__(576) k_unpack(const double *soa, double *aos, int B, int N) {
+  __shared__ double tile[18][33];
+  const int b0 = blockIdx.x * 32, tid = threadIdx.x;
+  for (int i = blockIdx.y; i < N; i += gridDim.y) {
+    {
+      const int bl = tid % 32, c = tid / 32;
+      if (c >= 1 && b0 + bl < B) tile[c][bl] = soa[(size_t(i) * 17 + (c - 1)) * B + b0 + bl];
+    }
+    __syncthreads();
+    {
+      const int c = tid % 18, bl = tid / 18;
+      if (c >= 1 && b0 + bl < B) aos[(size_t(b0 + bl) * N + i) * 18 + c] = tile[c][bl];
+    }
+    __syncthreads();
+  }
+}
+// Generic [B][N][W] <-> [N][W][B] (gains), one thread per element, writes coalesced.
+__global__ void k_transpose_bnw_to_nwb(const double *in, double *out, int B, int N, int W) {
+  const size_t total = size_t(B) * N * W;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += size_t(gridDim.x) * blockDim.x) {
+    const int b = int(e % B);
+    const size_t r = e / B;  // i*W + w
+    out[e] = in[size_t(b) * N * W + r];
+  }
+}
+__global__ void k_transpose_nwb_to_bnw(const double *in, double *out, int B, int N, int W) {
+  const size_t total = size_t(B) * N * W;
+  for (size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += size_t(gridDim.x) * blockDim.x) {
+    const int b = int(e % B);
+    const size_t r = e / B;
+    out[size_t(b) * N * W + r] = in[e];
+  }
+}
+
+// CostFunction::operator() with dense derivative outputs (cost.hh:36-61), AoS, for the API.
+__global__ void k_api_cost(const __grid_constant__ DeviceParams p, int B, const double *x, const double *u,
+                           const double *x_d, const double *u_d, double *cost, double *C_x, double *C_u,
+                           double *C_xx, double *C_uu, double *C_xu) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double xs[13], xd[13], du[4], dx[12], Jli[9];
+  for (int i = 0; i < 13; ++i) { xs[i] = x[size_t(b) * 13 + i]; xd[i] = x_d[size_t(b) * 13 + i]; }
+  for (int i = 0; i < 4; ++i) du[i] = u[size_t(b) * 4 + i] - u_d[size_t(b) * 4 + i];
+  state_minus(xs, xd, dx, Jli);
+  cost[b] = quadratic_cost(p, dx, du);
+  if (C_x || C_xx) {
+    double Ji[9], Qi[9], Cx[12], Cxx[144];
+    se3_rjacinv_blocks(dx, Jli, Ji, Qi);
+    cost_derivatives(p, dx, Ji, Qi, Cx, Cxx);
+    if (C_x) for (int i = 0; i < 12; ++i) C_x[size_t(b) * 12 + i] = Cx[i];
+    if (C_xx)
+      for (int r = 0; r < 12; ++r)
+        for (int c = 0; c < 12; ++c) C_xx[size_t(b) * 144 + 12 * r + c] = bel(Cxx, r, c);
+  }
+  if (C_u)
+    for (int j = 0; j < 4; ++j) {
+      double s = (2.0 * du[0]) * p.R[j];
+      for (int l = 1; l < 4; ++l) s = fma(2.0 * du[l], p.R[4 * l + j], s);
+      C_u[size_t(b) * 4 + j] = s;
+    }
+  if (C_uu) for (int e = 0; e < 16; ++e) C_uu[size_t(b) * 16 + e] = 2.0 * p.R[e];
+  if (C_xu) for (int e = 0; e < 48; ++e) C_xu[size_t(b) * 48 + e] = 0.0;
+}
+
+// Open-loop rollout under a constant control from per-problem initial states.
+__global__ void __launch_bounds__(128)
+k_rollout_constant(const __grid_constant__ DeviceParams p, const double *x0 /*[13][B]*/, double u0, double u1,
+                   double u2, double u3, double *traj, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[13];
+  const double u[4] = {u0, u1, u2, u3};
+#pragma unroll
+  for (int c = 0; c < 13; ++c) x[c] = x0[size_t(c) * B + b];
+  for (int i = 0; i < N; ++i) {
+    store_point(traj, i, B, b, x, u);
+    discrete_step(p, x, x + 3, x + 7, u);
+  }
+}
+
+}  // namespace qilqr
