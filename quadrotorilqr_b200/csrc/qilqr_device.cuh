@@ -117,11 +117,15 @@ QD void quat_to_rot(const double *q, double *R) {
   R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
 }
 // manif SO3::compose: Hamilton product + first-order renormalisation
+// The products are rounded individually (no FMA contraction) so that conj(q) (x) q has an
+// exactly zero vector part, as in the reference: x (-) x == 0 exactly (ilqr.hh:161 at knot 0).
 QD void quat_compose(const double *a, const double *b, double *r) {
-  double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
-  double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
-  double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
-  double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+#define QM(i, j) __dmul_rn(a[i], b[j])
+  double w = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 3), -QM(0, 0)), -QM(1, 1)), -QM(2, 2));
+  double x = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 0), QM(0, 3)), QM(1, 2)), -QM(2, 1));
+  double y = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 1), QM(1, 3)), QM(2, 0)), -QM(0, 2));
+  double z = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 2), QM(2, 3)), QM(0, 1)), -QM(1, 0));
+#undef QM
   const double sq = x * x + y * y + z * z + w * w;
   if (fabs(sq - 1.0) > kEps) {
     const double s = 2.0 / (1.0 + sq);
