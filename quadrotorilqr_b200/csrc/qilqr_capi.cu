@@ -9,12 +9,14 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "qilqr_api_kernels.cuh"
 #include "qilqr_kernels.cuh"
+#include "qilqr_backward_g4.cuh"
 
 using namespace qilqr;
 
@@ -56,6 +58,8 @@ struct qilqr_solver {
   int64_t launches = 0;
   qilqr_solve_stats_t stats{};
   bool profiling = false;
+  bool q_block_diagonal = true;  // Q = blkdiag(Q_pp, Q_vv): the 4-lanes-per-problem backward kernel applies
+  int g4_kpp = 4;                // knots linearised per phase by the quad kernel (1, 2 or 4)
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
 
@@ -191,6 +195,32 @@ int ensure_state(qilqr_solver *S, int B) {
 
 inline unsigned blocks_for(int n, int per) { return unsigned((n + per - 1) / per); }
 
+template <int KPP>
+void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
+  const size_t smem = sizeof(double) * g4::smem_doubles(KPP);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  k_backward_g4<KPP><<<blocks_for(ba.n, 8), 32, smem, S->stream>>>(S->p, ba);
+}
+// ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
+// coupling, one-thread-per-problem kernel otherwise.
+void launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
+  if (!S->q_block_diagonal) {
+    k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->stream>>>(S->p, ba);
+  } else if (S->g4_kpp == 1) {
+    launch_g4<1>(S, ba);
+  } else if (S->g4_kpp == 2) {
+    launch_g4<2>(S, ba);
+  } else {
+    launch_g4<4>(S, ba);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // The batched solve loop (device-resident data).
 // ---------------------------------------------------------------------------
@@ -231,7 +261,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     BackwardArgs ba{pr, st, active, n_active, i, 1, nullptr, nullptr};
     {
       SpanGuard g(S, 0);
-      k_backward_t1<<<blocks_for(n_active, 64), 64, 0, st_>>>(S->p, ba);
+      launch_backward(S, ba);
     }
     S->stats.backward_problem_knots += int64_t(n_active) * N;
     S->stats.problem_iterations += n_active;
@@ -376,6 +406,16 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   for (int i = 0; i < 144; ++i) p.Q[i] = Q[i];
   for (int i = 0; i < 16; ++i) p.R[i] = R[i];
   S->p = p;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 6; j < 12; ++j)
+      if (Q[12 * i + j] != 0.0 || Q[12 * j + i] != 0.0) S->q_block_diagonal = false;
+  if (const char *e = std::getenv("QILQR_BACKWARD")) {  // debugging aid: "t1" forces the per-thread kernel
+    if (std::string(e) == "t1") S->q_block_diagonal = false;
+  }
+  if (const char *e = std::getenv("QILQR_KPP")) {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4) S->g4_kpp = v;
+  }
   S->opt = *options;
   apply_options(S);
   if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -603,7 +643,7 @@ int qilqr_backwards_pass_host(qilqr_solver_t *S, int B, int N, const double *des
   if (rc) return rc;
   Problem pr{B, N, Bd, nullptr, nullptr, S->desired_soa.as<double>(), S->gk.as<double>(), S->gK.as<double>()};
   BackwardArgs ba{pr, SolveState{}, nullptr, B, 0, 0, S->traj_soa.as<double>(), S->misc.as<double>()};
-  k_backward_t1<<<blocks_for(B, 64), 64, 0, st_>>>(S->p, ba);
+  launch_backward(S, ba);
   ++S->launches;
   transpose_to_aos(S, S->gk.as<double>(), S->stage_c.as<double>(), B, N, 4);
   QCUDA(S, cudaMemcpyAsync(k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
