@@ -87,11 +87,12 @@ __global__ void k_api_state_minus(int B, const double *lhs, const double *rhs, d
   if (b >= B) return;
   double l[13], r[13], d[12], Jli[9];
   for (int i = 0; i < 13; ++i) { l[i] = lhs[size_t(b) * 13 + i]; r[i] = rhs[size_t(b) * 13 + i]; }
-  state_minus(l, r, d, Jli);
+  Angle ang;
+  state_minus(l, r, d, Jli, &ang);
   for (int i = 0; i < 12; ++i) out[size_t(b) * 12 + i] = d[i];
   if (J_lhs) {
     double Ji[9], Qi[9];
-    se3_rjacinv_blocks(d, Jli, Ji, Qi);
+    se3_rjacinv_blocks(d, Jli, ang, Ji, Qi);
     double *J = J_lhs + size_t(b) * 144;
     zero_fill(J, 144);
     put_block(J, 12, 0, 0, Ji);

@@ -84,8 +84,9 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
     st9(rec + R_WD, A.Wd);
   }
   double dx[12], Jli[9], Ji[9], Qi[9];
-  state_minus(x, xd, dx, Jli);
-  se3_rjacinv_blocks(dx, Jli, Ji, Qi);
+  Angle ang;
+  state_minus(x, xd, dx, Jli, &ang);
+  se3_rjacinv_blocks(dx, Jli, ang, Ji, Qi);
   // y = (2 dx)^T Q with Q = blkdiag(Qpp, Qvv)
   double y[12];
 #pragma unroll

@@ -154,24 +154,33 @@ QD void so3_jac_from_coeffs(const double *w, double a, double b, double *J) {
   J[3] = fma(b, WW[3], a * w[2]);     J[4] = fma(b, WW[4], 1.0);       J[5] = fma(b, WW[5], -a * w[0]);
   J[6] = fma(b, WW[6], -a * w[1]);    J[7] = fma(b, WW[7], a * w[0]);  J[8] = fma(b, WW[8], 1.0);
 }
+// theta^2, theta, sin(theta), cos(theta) of a rotation vector, evaluated once and shared by the
+// Jacobians that manif evaluates separately (ljac/ljacinv/fillQ all use the same theta).
+struct Angle {
+  double th2, th, s, c;  // th, s, c are meaningful only when th2 > kEps
+};
+QD Angle angle_of(const double *w) {
+  Angle a;
+  a.th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  a.th = 0.0; a.s = 0.0; a.c = 1.0;
+  if (a.th2 > kEps) {
+    a.th = sqrt(a.th2);
+    sincos(a.th, &a.s, &a.c);
+  }
+  return a;
+}
 // manif SO3Tangent::ljac
-QD void so3_ljac(const double *w, double *J) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-  if (th2 <= kEps) { so3_jac_from_coeffs(w, 0.5, 0.0, J); return; }
-  const double th = sqrt(th2);
-  double s, c;
-  sincos(th, &s, &c);
-  so3_jac_from_coeffs(w, (1.0 - c) / th2, (th - s) / (th2 * th), J);
+QD void so3_ljac(const double *w, const Angle &a, double *J) {
+  if (a.th2 <= kEps) { so3_jac_from_coeffs(w, 0.5, 0.0, J); return; }
+  so3_jac_from_coeffs(w, (1.0 - a.c) / a.th2, (a.th - a.s) / (a.th2 * a.th), J);
 }
+QD void so3_ljac(const double *w, double *J) { so3_ljac(w, angle_of(w), J); }
 // manif SO3Tangent::ljacinv;  rjacinv is its transpose
-QD void so3_ljacinv(const double *w, double *J) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
-  if (th2 <= kEps) { so3_jac_from_coeffs(w, -0.5, 0.0, J); return; }
-  const double th = sqrt(th2);
-  double s, c;
-  sincos(th, &s, &c);
-  so3_jac_from_coeffs(w, -0.5, 1.0 / th2 - (1.0 + c) / (2.0 * th * s), J);
+QD void so3_ljacinv(const double *w, const Angle &a, double *J) {
+  if (a.th2 <= kEps) { so3_jac_from_coeffs(w, -0.5, 0.0, J); return; }
+  so3_jac_from_coeffs(w, -0.5, 1.0 / a.th2 - (1.0 + a.c) / (2.0 * a.th * a.s), J);
 }
+QD void so3_ljacinv(const double *w, double *J) { so3_ljacinv(w, angle_of(w), J); }
 // manif SO3Tangent::exp
 QD void so3_exp(const double *w, double *q) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
@@ -199,17 +208,16 @@ QD void so3_log(const double *q, double *w) {
 }
 
 // manif SE3Tangent::fillQ (Barfoot's Q block, manif's arrangement), for tangent (v, w)
-QD void se3_fillQ(const double *v, const double *w, double *Q) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+// (`a` = angle_of(w); the angle of -w is the same)
+QD void se3_fillQ(const double *v, const double *w, const Angle &a, double *Q) {
+  const double th2 = a.th2;
   double B, C, D;
   if (th2 <= kEps) {
     B = 1.0 / 6.0 + (1.0 / 120.0) * th2;
     C = -(1.0 / 24.0) + (1.0 / 720.0) * th2;
     D = -(1.0 / 60.0);
   } else {
-    const double th = sqrt(th2);
-    double s, c;
-    sincos(th, &s, &c);
+    const double th = a.th, s = a.s, c = a.c;
     B = (th - s) / (th2 * th);
     C = (1.0 - th2 / 2.0 - c) / (th2 * th2);
     D = C - 3.0 * (th - s - th2 * th / 6.0) / (th2 * th2 * th);
@@ -236,6 +244,7 @@ QD void se3_fillQ(const double *v, const double *w, double *Q) {
       Q[ij] = ((t1 + t2) - t3) - t4;
     }
 }
+QD void se3_fillQ(const double *v, const double *w, double *Q) { se3_fillQ(v, w, angle_of(w), Q); }
 
 // ---------------------------------------------------------------------------
 // SE(3) pose = t[3], q[4].
@@ -244,7 +253,7 @@ QD void se3_fillQ(const double *v, const double *w, double *Q) {
 // Optionally returns Jl^-1(w) (3x3) so callers can build Jr^-1 blocks without
 // recomputing the trigonometry.
 QD void se3_rminus(const double *tA, const double *qA, const double *tB, const double *qB,
-                   double *tau, double *Jlinv_out /* may be nullptr */) {
+                   double *tau, double *Jlinv_out /* may be nullptr */, Angle *angle_out = nullptr) {
   // inverse(B) = (-R_B^T t_B, conj(q_B))
   double RB[9];
   quat_to_rot(qB, RB);
@@ -262,7 +271,9 @@ QD void se3_rminus(const double *tA, const double *qA, const double *tB, const d
   double w[3];
   so3_log(qrel, w);
   double Jli[9];
-  so3_ljacinv(w, Jli);
+  const Angle ang = angle_of(w);
+  if (angle_out) *angle_out = ang;
+  so3_ljacinv(w, ang, Jli);
   m3_vec(Jli, trel, tau);
   tau[3] = w[0]; tau[4] = w[1]; tau[5] = w[2];
   if (Jlinv_out) {
@@ -273,11 +284,11 @@ QD void se3_rminus(const double *tA, const double *qA, const double *tB, const d
 
 // Blocks of the SE(3) right-Jacobian inverse at tau (manif SE3Tangent::rjacinv):
 //   Jr^-1(tau) = [[Ji, Qi], [0, Ji]],  Ji = Jr^-1(w) = Jl^-1(w)^T,  Qi = -Ji Q(-tau) Ji
-QD void se3_rjacinv_blocks(const double *tau, const double *Jlinv, double *Ji, double *Qi) {
+QD void se3_rjacinv_blocks(const double *tau, const double *Jlinv, const Angle &ang, double *Ji, double *Qi) {
   m3_transpose(Jlinv, Ji);
   const double nv[3] = {-tau[0], -tau[1], -tau[2]}, nw[3] = {-tau[3], -tau[4], -tau[5]};
   double Qm[9], T[9];
-  se3_fillQ(nv, nw, Qm);
+  se3_fillQ(nv, nw, ang, Qm);
   m3_mul(Ji, Qm, T);
   m3_mul(T, Ji, Qi);
 #pragma unroll
@@ -362,7 +373,8 @@ QD void se3_plus_blocks(const double *tau, double *Re, double *Te, double *Jr, d
                         double *qe) {
   const double *v = tau, *w = tau + 3;
   double Jl[9], RE[9];
-  so3_ljac(w, Jl);
+  const Angle ang = angle_of(w);
+  so3_ljac(w, ang, Jl);
   m3_vec(Jl, v, te);
   so3_exp(w, qe);
   quat_to_rot(qe, RE);
@@ -374,7 +386,7 @@ QD void se3_plus_blocks(const double *tau, double *Re, double *Te, double *Jr, d
   m3_hat_mul(tinv, Re, Te);
   m3_transpose(Jl, Jr);
   const double nv[3] = {-v[0], -v[1], -v[2]}, nw[3] = {-w[0], -w[1], -w[2]};
-  se3_fillQ(nv, nw, Qb);
+  se3_fillQ(nv, nw, ang, Qb);
 }
 // Continuous-time Jacobian pieces (quadrotor_model.cc:88-111):
 //   gz = -g R^T e_z  (G = hat(gz)),   Wc = -I^-1 (hat(w) I - hat(I w))
@@ -424,8 +436,9 @@ QD void dynamics_blocks(const DeviceParams &p, const double *q, const double *ve
 // Tracking cost (cost.hh:36-61)
 // ---------------------------------------------------------------------------
 // delta_x = x (-) x_d  as 12 coefficients [Log(x_d^-1 x); v - v_d]
-QD void state_minus(const double *x /*13*/, const double *xd /*13*/, double *dx /*12*/, double *Jlinv) {
-  se3_rminus(x, x + 3, xd, xd + 3, dx, Jlinv);
+QD void state_minus(const double *x /*13*/, const double *xd /*13*/, double *dx /*12*/, double *Jlinv,
+                    Angle *angle_out = nullptr) {
+  se3_rminus(x, x + 3, xd, xd + 3, dx, Jlinv, angle_out);
 #pragma unroll
   for (int i = 0; i < 6; ++i) dx[6 + i] = x[7 + i] - xd[7 + i];
 }

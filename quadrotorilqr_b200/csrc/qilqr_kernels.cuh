@@ -198,79 +198,96 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceP
 }
 
 // ---------------------------------------------------------------------------
-// Eigen::LDLT<Matrix4d> semantics (pivot on the largest remaining |diagonal|,
-// lower triangle only, D pseudo-inverse) -- ilqr.hh:126-128.  m: row-major 4x4.
+// Eigen::LDLT<Matrix4d> semantics -- ilqr.hh:126-128: symmetric pivoting on the largest
+// remaining |diagonal|, lower triangle only, D pseudo-inverse.  Eigen's kernel is
+// left-looking, so the pivot order depends only on the ORIGINAL diagonal: all (predicated)
+// symmetric swaps are applied up front and the factorisation itself is straight-line code
+// on registers (no local memory, no branches).  Divisions by the pivots are done as
+// multiplications by their reciprocals (<= 1 ulp away from Eigen's divisions).
+// m: row-major 4x4, only the lower triangle is read.
 // ---------------------------------------------------------------------------
 struct Ldlt4 {
   double m[16];
-  int tr[4];
+  double l10, l20, l21, l30, l31, l32;
+  double dinv[4];  // 1/d_i, or 0 where |d_i| <= DBL_MIN (Eigen's pseudo-inverse of D)
+  bool s01, s02, s03, s12, s13, s23;
 };
+QD void cswap(bool c, double &a, double &b) {
+  const double t = a;
+  a = c ? b : a;
+  b = c ? t : b;
+}
 QD void ldlt4_compute(Ldlt4 &f) {
-  double *m = f.m;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    int piv = k;
-    double best = fabs(m[5 * k]);
-#pragma unroll
-    for (int i = k + 1; i < 4; ++i) {
-      const double v = fabs(m[5 * i]);
-      if (v > best) { best = v; piv = i; }
-    }
-    f.tr[k] = piv;
-    if (piv != k) {
-      for (int j = 0; j < k; ++j) { const double t = m[4 * k + j]; m[4 * k + j] = m[4 * piv + j]; m[4 * piv + j] = t; }
-      for (int i = piv + 1; i < 4; ++i) { const double t = m[4 * i + k]; m[4 * i + k] = m[4 * i + piv]; m[4 * i + piv] = t; }
-      { const double t = m[5 * k]; m[5 * k] = m[5 * piv]; m[5 * piv] = t; }
-      for (int i = k + 1; i < piv; ++i) { const double t = m[4 * i + k]; m[4 * i + k] = m[4 * piv + i]; m[4 * piv + i] = t; }
-    }
-    if (k > 0) {
-      double temp[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) if (j < k) temp[j] = m[5 * j] * m[4 * k + j];
-      double acc = m[4 * k] * temp[0];
-#pragma unroll
-      for (int j = 1; j < 3; ++j) if (j < k) acc = fma(m[4 * k + j], temp[j], acc);
-      m[5 * k] = m[5 * k] - acc;
-#pragma unroll
-      for (int i = k + 1; i < 4; ++i) {
-        double a2 = m[4 * i] * temp[0];
-#pragma unroll
-        for (int j = 1; j < 3; ++j) if (j < k) a2 = fma(m[4 * i + j], temp[j], a2);
-        m[4 * i + k] = m[4 * i + k] - a2;
-      }
-    }
-    const double akk = m[5 * k];
-    const bool valid = fabs(akk) > 0.0;
-    if (k == 0 && !valid) {
-      f.tr[0] = 0; f.tr[1] = 1; f.tr[2] = 2; f.tr[3] = 3;
-      return;
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = k + 1; i < 4; ++i) m[4 * i + k] = m[4 * i + k] / akk;
-    }
+  const double *m = f.m;
+  double a00 = m[0], a10 = m[4], a11 = m[5], a20 = m[8], a21 = m[9], a22 = m[10], a30 = m[12], a31 = m[13],
+         a32 = m[14], a33 = m[15];
+  {  // step 0: first maximum of |a00|,|a11|,|a22|,|a33|
+    double best = fabs(a00);
+    int p = 0;
+    if (fabs(a11) > best) { best = fabs(a11); p = 1; }
+    if (fabs(a22) > best) { best = fabs(a22); p = 2; }
+    if (fabs(a33) > best) { p = 3; }
+    f.s01 = p == 1; f.s02 = p == 2; f.s03 = p == 3;
+    cswap(f.s01, a00, a11); cswap(f.s01, a20, a21); cswap(f.s01, a30, a31);
+    cswap(f.s02, a00, a22); cswap(f.s02, a10, a21); cswap(f.s02, a30, a32);
+    cswap(f.s03, a00, a33); cswap(f.s03, a10, a31); cswap(f.s03, a20, a32);
   }
+  {  // step 1: first maximum of |a11|,|a22|,|a33|
+    double best = fabs(a11);
+    int p = 1;
+    if (fabs(a22) > best) { best = fabs(a22); p = 2; }
+    if (fabs(a33) > best) { p = 3; }
+    f.s12 = p == 2; f.s13 = p == 3;
+    cswap(f.s12, a10, a20); cswap(f.s12, a11, a22); cswap(f.s12, a31, a32);
+    cswap(f.s13, a10, a30); cswap(f.s13, a11, a33); cswap(f.s13, a21, a32);
+  }
+  {  // step 2
+    f.s23 = fabs(a33) > fabs(a22);
+    cswap(f.s23, a20, a30); cswap(f.s23, a21, a31); cswap(f.s23, a22, a33);
+  }
+  const double kMin = 2.2250738585072014e-308;
+  const double d0 = a00;
+  const double r0 = 1.0 / d0;
+  const bool v0 = fabs(d0) > 0.0;
+  const double l10 = v0 ? a10 * r0 : a10, l20 = v0 ? a20 * r0 : a20, l30 = v0 ? a30 * r0 : a30;
+  double t0 = d0 * l10;
+  const double d1 = a11 - l10 * t0;
+  const double m21 = a21 - l20 * t0, m31 = a31 - l30 * t0;
+  const double r1 = 1.0 / d1;
+  const bool v1 = fabs(d1) > 0.0;
+  const double l21 = v1 ? m21 * r1 : m21, l31 = v1 ? m31 * r1 : m31;
+  t0 = d0 * l20;
+  double t1 = d1 * l21;
+  const double d2 = a22 - fma(l21, t1, l20 * t0);
+  t0 = d0 * l30;
+  const double t1b = d1 * l31;
+  const double m32 = a32 - fma(l31, t1, l30 * (d0 * l20));
+  const double r2 = 1.0 / d2;
+  const bool v2 = fabs(d2) > 0.0;
+  const double l32 = v2 ? m32 * r2 : m32;
+  const double t2 = d2 * l32;
+  const double d3 = a33 - fma(l32, t2, fma(l31, t1b, l30 * t0));
+  f.l10 = l10; f.l20 = l20; f.l21 = l21; f.l30 = l30; f.l31 = l31; f.l32 = l32;
+  f.dinv[0] = fabs(d0) > kMin ? r0 : 0.0;
+  f.dinv[1] = fabs(d1) > kMin ? r1 : 0.0;
+  f.dinv[2] = fabs(d2) > kMin ? r2 : 0.0;
+  f.dinv[3] = fabs(d3) > kMin ? 1.0 / d3 : 0.0;
 }
 QD void ldlt4_solve(const Ldlt4 &f, double *x /*4, in place*/) {
-  const double *m = f.m;
+  cswap(f.s01, x[0], x[1]); cswap(f.s02, x[0], x[2]); cswap(f.s03, x[0], x[3]);
+  cswap(f.s12, x[1], x[2]); cswap(f.s13, x[1], x[3]);
+  cswap(f.s23, x[2], x[3]);
+  x[1] = x[1] - f.l10 * x[0];
+  x[2] = x[2] - f.l20 * x[0] - f.l21 * x[1];
+  x[3] = x[3] - f.l30 * x[0] - f.l31 * x[1] - f.l32 * x[2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int t = f.tr[k];
-    if (t != k) { const double s = x[k]; x[k] = x[t]; x[t] = s; }
-  }
-  x[1] = x[1] - m[4] * x[0];
-  x[2] = x[2] - m[8] * x[0] - m[9] * x[1];
-  x[3] = x[3] - m[12] * x[0] - m[13] * x[1] - m[14] * x[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = (fabs(m[5 * i]) > 2.2250738585072014e-308) ? x[i] / m[5 * i] : 0.0;
-  x[2] = x[2] - m[14] * x[3];
-  x[1] = x[1] - m[9] * x[2] - m[13] * x[3];
-  x[0] = x[0] - m[4] * x[1] - m[8] * x[2] - m[12] * x[3];
-#pragma unroll
-  for (int k = 3; k >= 0; --k) {
-    const int t = f.tr[k];
-    if (t != k) { const double s = x[k]; x[k] = x[t]; x[t] = s; }
-  }
+  for (int i = 0; i < 4; ++i) x[i] = x[i] * f.dinv[i];
+  x[2] = x[2] - f.l32 * x[3];
+  x[1] = x[1] - f.l21 * x[2] - f.l31 * x[3];
+  x[0] = x[0] - f.l10 * x[1] - f.l20 * x[2] - f.l30 * x[3];
+  cswap(f.s23, x[2], x[3]);
+  cswap(f.s13, x[1], x[3]); cswap(f.s12, x[1], x[2]);
+  cswap(f.s03, x[0], x[3]); cswap(f.s02, x[0], x[2]); cswap(f.s01, x[0], x[1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -368,8 +385,9 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
     dynamics_blocks(p, x + 3, x + 7, A);
 
     double dx[12], Jli[9], Ji[9], Qi[9];
-    state_minus(x, xd, dx, Jli);
-    se3_rjacinv_blocks(dx, Jli, Ji, Qi);
+    Angle ang;
+    state_minus(x, xd, dx, Jli, &ang);
+    se3_rjacinv_blocks(dx, Jli, ang, Ji, Qi);
     double Cx[12], Qxx[144];
     cost_derivatives(p, dx, Ji, Qi, Cx, Qxx);  // Qxx starts as C.xx
     double Cu[4];
@@ -748,11 +766,12 @@ __global__ void k_api_cost(const __grid_constant__ DeviceParams p, int B, const 
   double xs[13], xd[13], du[4], dx[12], Jli[9];
   for (int i = 0; i < 13; ++i) { xs[i] = x[size_t(b) * 13 + i]; xd[i] = x_d[size_t(b) * 13 + i]; }
   for (int i = 0; i < 4; ++i) du[i] = u[size_t(b) * 4 + i] - u_d[size_t(b) * 4 + i];
-  state_minus(xs, xd, dx, Jli);
+  Angle ang;
+  state_minus(xs, xd, dx, Jli, &ang);
   cost[b] = quadratic_cost(p, dx, du);
   if (C_x || C_xx) {
     double Ji[9], Qi[9], Cx[12], Cxx[144];
-    se3_rjacinv_blocks(dx, Jli, Ji, Qi);
+    se3_rjacinv_blocks(dx, Jli, ang, Ji, Qi);
     cost_derivatives(p, dx, Ji, Qi, Cx, Cxx);
     if (C_x) for (int i = 0; i < 12; ++i) C_x[size_t(b) * 12 + i] = Cx[i];
     if (C_xx)
