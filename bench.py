@@ -170,6 +170,9 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-serial", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -196,30 +199,66 @@ def main():
     torch.cuda.set_device(dev)
 
     m, opts = problems.hover_model(), problems.default_options(False)
-    solver = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
-                       m["Q"], m["R"], m["dt_s"], opts, device=local_rank)
-    solver.set_profiling(True)
     B, N = args.batch, N_KNOTS
-    stream = torch.cuda.ExternalStream(solver.stream_handle, device=dev)
+    P = max(1, args.pipeline)
+
+    def make_solver():
+        s_ = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
+                       m["Q"], m["R"], m["dt_s"], opts, device=local_rank)
+        s_.set_profiling(True)
+        return s_
+
+    # P solver handles = a P-deep software pipeline of batches: each handle is driven by its own host
+    # thread on its own stream, so the latency-bound tail of one batch (the few problems that run to
+    # max_iters) overlaps the throughput-bound bulk of the next.  Every step is still one full batch.
+    solvers = [make_solver() for _ in range(P)]
+    streams = [torch.cuda.ExternalStream(s_.stream_handle, device=dev) for s_ in solvers]
+    solver = solvers[0]
 
     # ---- synthetic inputs: this rank's problems [rank*B, (rank+1)*B) of the Philox stream ----
     desired = problems.hover_desired_trajectory(N, m["dt_s"], m["mass_kg"], m["g_mpss"])
     x0 = problems.hover_initial_states(B, seed=args.seed, first=rank * B)
     x0_soa = torch.from_numpy(np.ascontiguousarray(x0.T)).to(dev)  # [13][B]
     init_soa = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
-    work_soa = torch.empty_like(init_soa)
+    work_soa = [torch.empty_like(init_soa) for _ in range(P)]
     des_aos = torch.from_numpy(desired[None].copy()).to(dev)
     des_soa = torch.empty((N, 17, 1), dtype=torch.float64, device=dev)
-    res_dev = torch.zeros(B * 24, dtype=torch.uint8, device=dev)
+    res_dev = [torch.zeros(B * 24, dtype=torch.uint8, device=dev) for _ in range(P)]
     torch.cuda.synchronize()
     solver.pack_trajectory_device(des_aos, des_soa)
     solver.rollout_constant_control_device(x0_soa, desired[0, 14:18], init_soa)  # open-loop hover rollout
     torch.cuda.synchronize()
 
-    def device_step():
-        with torch.cuda.stream(stream):
-            work_soa.copy_(init_soa, non_blocking=True)
-        solver.solve_device(work_soa, des_soa, results=res_dev)
+    STAT_KEYS = ("backward_ms", "rollout_ms", "backward_problem_knots", "rollout_problem_knots",
+                 "problem_iterations", "problem_rollouts", "solver_iterations")
+
+    def device_step(j, acc=None):
+        with torch.cuda.stream(streams[j]):
+            work_soa[j].copy_(init_soa, non_blocking=True)
+        solvers[j].solve_device(work_soa[j], des_soa, results=res_dev[j])
+        if acc is not None:
+            st = solvers[j].last_solve_stats()
+            for k_ in STAT_KEYS:
+                acc[k_] += st[k_]
+
+    def run_pipelined(step_fn, nsteps):
+        """Issue `nsteps` steps round-robin over the P handles, one host thread per handle."""
+        accs = [{k_: 0 for k_ in STAT_KEYS} for _ in range(P)]
+        counts = [nsteps // P + (1 if j < nsteps % P else 0) for j in range(P)]
+
+        def worker(j):
+            for _ in range(counts[j]):
+                step_fn(j, accs[j])
+
+        if P == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(j,)) for j in range(P)]
+            for t_ in ths:
+                t_.start()
+            for t_ in ths:
+                t_.join()
+        return {k_: sum(a_[k_] for a_ in accs) for k_ in STAT_KEYS}
 
     def barrier():
         if dist is not None:
@@ -227,45 +266,49 @@ def main():
         torch.cuda.synchronize()
 
     # ---- `value`: device-resident ----------------------------------------------------------
-    for _ in range(args.warmup):
-        device_step()
+    run_pipelined(device_step, max(args.warmup, P))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = solver.kernel_launch_count
-    bwd_ms = roll_ms = 0.0
-    bwd_knots = roll_knots = prob_iters = prob_rollouts = solver_iters = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sum(s_.kernel_launch_count for s_ in solvers)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
     barrier()
-    ev0.record(stream)
+    for j in range(P):
+        ev0[j].record(streams[j])
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        device_step()
-        st = solver.last_solve_stats()
-        bwd_ms += st["backward_ms"]
-        roll_ms += st["rollout_ms"]
-        bwd_knots += st["backward_problem_knots"]
-        roll_knots += st["rollout_problem_knots"]
-        prob_iters += st["problem_iterations"]
-        prob_rollouts += st["problem_rollouts"]
-        solver_iters += st["solver_iterations"]
-    ev1.record(stream)
+    tot = run_pipelined(device_step, args.steps)
+    for j in range(P):
+        ev1[j].record(streams[j])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = solver.kernel_launch_count - launches0
+    launches = sum(s_.kernel_launch_count for s_ in solvers) - launches0
     clocks = sampler.stop()
-    dev_ms = ev0.elapsed_time(ev1)
-    res = np.frombuffer(res_dev.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    dev_ms = max(ev0[j].elapsed_time(ev1[j]) for j in range(P))
+    bwd_ms, roll_ms = tot["backward_ms"], tot["rollout_ms"]
+    bwd_knots, roll_knots = tot["backward_problem_knots"], tot["rollout_problem_knots"]
+    prob_iters, prob_rollouts, solver_iters = tot["problem_iterations"], tot["problem_rollouts"], tot["solver_iterations"]
+    res = np.frombuffer(res_dev[0].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     converged = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
     ls_failed = int(np.sum(res["status"] == 4))
     max_iter_hit = int(np.sum(res["status"] == 3))
+
+    # one batch at a time on one handle (no pipelining), for reference
+    serial_ms = None
+    if P > 1 and not args.no_serial:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            device_step(0)
+        torch.cuda.synchronize()
+        serial_ms = 1e3 * (time.perf_counter() - t0) / 2
 
     # ---- `e2e`: host buffers through qilqr_solve_host ------------------------------------------
     e2e = None
     if not args.no_e2e:
         init_host = torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True)
-        out_host = torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True)
-        res_host = torch.zeros(B * 24, dtype=torch.uint8, pin_memory=True)
+        out_host = [torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True) for _ in range(P)]
+        res_host = [torch.zeros(B * 24, dtype=torch.uint8, pin_memory=True) for _ in range(P)]
         aos = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
         solver.unpack_trajectory_device(init_soa, aos, time_src=None)
@@ -274,17 +317,18 @@ def main():
         init_host[:, :, 0] = torch.arange(N, dtype=torch.float64) * m["dt_s"]
         del aos
         desired_c = np.ascontiguousarray(desired)
-        e2e_warm = max(1, min(args.warmup, 2))
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_warm):
-            solver.solve_host_buffers(init_host, desired_c, out_host, res_host)
+
+        def host_step(j, acc=None):
+            solvers[j].solve_host_buffers(init_host, desired_c, out_host[j], res_host[j])
+
+        e2e_steps = max(P, min(args.steps, 4))
+        run_pipelined(host_step, P)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            solver.solve_host_buffers(init_host, desired_c, out_host, res_host)
+        run_pipelined(host_step, e2e_steps)
         barrier()
         e2e_t = time.perf_counter() - t0
-        r2 = np.frombuffer(res_host.numpy().tobytes(), dtype=RESULT_DTYPE)
+        r2 = np.frombuffer(res_host[0].numpy().tobytes(), dtype=RESULT_DTYPE)
         conv2 = int(np.sum((r2["status"] == 1) | (r2["status"] == 2)))
         e2e = {"t": e2e_t, "steps": e2e_steps, "converged": conv2,
                "h2d": B * N * 18 * 8 + N * 18 * 8, "d2h": B * N * 18 * 8 + B * 24}
@@ -356,7 +400,11 @@ def main():
                                "torque_to_thrust_ratio=0.1, x0: pos U[-1,1]^3, angle U[0,0.5] rad, vel U[-0.25,0.25]^6 "
                                f"(Philox seed {args.seed})",
                    "cache": "inputs larger than L2 (356 MB trajectories + 1.4 GB gains per step vs 126 MB L2)",
-                   "parallelism": f"{world} independent shard(s), one process per GPU"},
+                   "parallelism": f"{world} independent shard(s), one process per GPU",
+                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream each); "
+                               "each step is one full batch"},
+        "serial_ms_per_step": serial_ms,
+        "serial_value": (converged / (serial_ms * 1e-3)) if serial_ms else None,
         "us_per_iteration": us_per_iter,
         "converged_fraction": total_converged_per_step / (B * world),
         "line_search_failures": int(sm[4]), "max_iters_hit": int(sm[5]),

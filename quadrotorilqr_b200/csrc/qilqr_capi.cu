@@ -53,7 +53,11 @@ struct qilqr_solver {
   DeviceParams p{};
   qilqr_options_t opt{};
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // bulk work, lowest priority
+  cudaStream_t stream_hi = nullptr;  // the latency-bound tail of a solve (few problems left), highest priority
+  cudaStream_t cur = nullptr;        // the one solve_core is currently launching on
+  cudaEvent_t ev_switch = nullptr;
+  int hi_threshold = 2048;           // switch to stream_hi when at most this many problems are active
   std::string last_error;
   int64_t launches = 0;
   qilqr_solve_stats_t stats{};
@@ -105,12 +109,12 @@ struct SpanGuard {
       sp.start = get_event(S);
       sp.stop = get_event(S);
       sp.kind = kind;
-      cudaEventRecord(sp.start, S->stream);
+      cudaEventRecord(sp.start, S->cur);
     }
   }
   ~SpanGuard() {
     if (on) {
-      cudaEventRecord(sp.stop, S->stream);
+      cudaEventRecord(sp.stop, S->cur);
       S->spans.push_back(sp);
     }
   }
@@ -205,13 +209,13 @@ void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  k_backward_g4<KPP><<<blocks_for(ba.n, 8), 32, smem, S->stream>>>(S->p, ba);
+  k_backward_g4<KPP><<<blocks_for(ba.n, 8), 32, smem, S->cur>>>(S->p, ba);
 }
 // ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
 // coupling, one-thread-per-problem kernel otherwise.
 void launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
   if (!S->q_block_diagonal) {
-    k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->stream>>>(S->p, ba);
+    k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->cur>>>(S->p, ba);
   } else if (S->g4_kpp == 1) {
     launch_g4<1>(S, ba);
   } else if (S->g4_kpp == 2) {
@@ -257,7 +261,17 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   int n_active = B;
   const int *active = nullptr;  // nullptr = identity list
   int cur = 0;
+  bool on_hi = false;
   for (int i = 0; i < S->opt.max_iters && n_active > 0; ++i) {  // ilqr.hh:58 (max_iters is a double)
+    if (!on_hi && n_active <= S->hi_threshold && B > S->hi_threshold) {
+      // Few problems left: every further iteration is a chain of tiny, latency-bound launches.  Move them
+      // to the high-priority stream so that they are not queued behind another handle's bulk kernels.
+      cudaEventRecord(S->ev_switch, st_);
+      cudaStreamWaitEvent(S->stream_hi, S->ev_switch, 0);
+      st_ = S->stream_hi;
+      S->cur = st_;
+      on_hi = true;
+    }
     BackwardArgs ba{pr, st, active, n_active, i, 1, nullptr, nullptr};
     {
       SpanGuard g(S, 0);
@@ -311,7 +325,12 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     k_collect<<<grid, 128, 0, st_>>>(pr, st.sel);
   }
   S->launches += 2;
-  QCUDA(S, cudaStreamSynchronize(st_));
+  if (on_hi) {  // rejoin the solver's main stream
+    cudaEventRecord(S->ev_switch, st_);
+    cudaStreamWaitEvent(S->stream, S->ev_switch, 0);
+    S->cur = S->stream;
+  }
+  QCUDA(S, cudaStreamSynchronize(S->stream));
   QCUDA(S, cudaGetLastError());
   S->stats.kernel_launches = S->launches - launches0;
   return QILQR_OK;
@@ -418,12 +437,18 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   }
   S->opt = *options;
   apply_options(S);
-  if (cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (const char *e = std::getenv("QILQR_HI_THRESHOLD")) S->hi_threshold = std::atoi(e);
+  if (cudaStreamCreateWithPriority(&S->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&S->stream_hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+      cudaEventCreateWithFlags(&S->ev_switch, cudaEventDisableTiming) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void **>(&S->h_counts), 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(reinterpret_cast<void **>(&S->d_counts), S->h_counts, 0) != cudaSuccess) {
     delete S;
     return QILQR_ERR_CUDA;
   }
+  S->cur = S->stream;
   *out = S;
   return QILQR_OK;
 }
@@ -438,6 +463,8 @@ void qilqr_destroy(qilqr_solver_t *S) {
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
+  if (S->ev_switch) cudaEventDestroy(S->ev_switch);
+  if (S->stream_hi) cudaStreamDestroy(S->stream_hi);
   if (S->stream) cudaStreamDestroy(S->stream);
   delete S;
 }
