@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(32) k_backward_g4(const __grid_constant__ Devi
   } else {
     st.alpha[b] = 1.0;
     st.ls_iter[b] = 0;
-    st.phase[b] = PHASE_SEARCH;
+    st.phase[b] = a.search_phase;
   }
 }
 

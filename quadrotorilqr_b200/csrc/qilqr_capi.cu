@@ -69,7 +69,7 @@ struct qilqr_solver {
 
   // workspace
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
-      hist_d, debug_d, misc;
+      hist_d, debug_d, misc, wide_d;
   int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
   int *d_counts = nullptr;
 };
@@ -193,7 +193,7 @@ SolveState make_state(qilqr_solver *S, int B, double *hist, int hist_cap) {
 int ensure_state(qilqr_solver *S, int B) {
   QCUDA(S, S->state_d.ensure(sizeof(double) * StateLayout::kDoubles * size_t(B)));
   QCUDA(S, S->state_i.ensure(sizeof(int) * StateLayout::kInts * size_t(B)));
-  QCUDA(S, S->lists.ensure(sizeof(int) * 4 * size_t(B)));
+  QCUDA(S, S->lists.ensure(sizeof(int) * 5 * size_t(B)));
   return QILQR_OK;
 }
 
@@ -262,6 +262,9 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   const int *active = nullptr;  // nullptr = identity list
   int cur = 0;
   bool on_hi = false;
+  const int P_alpha = S->opt.num_parallel_alphas > 1 ? S->opt.num_parallel_alphas : 1;
+  int *listF = S->lists.as<int>() + 4 * size_t(B);
+  if (P_alpha > 1) QCUDA(S, S->wide_d.ensure(sizeof(double) * size_t(P_alpha) * B));
   for (int i = 0; i < S->opt.max_iters && n_active > 0; ++i) {  // ilqr.hh:58 (max_iters is a double)
     if (!on_hi && n_active <= S->hi_threshold && B > S->hi_threshold) {
       // Few problems left: every further iteration is a chain of tiny, latency-bound launches.  Move them
@@ -272,42 +275,77 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       S->cur = st_;
       on_hi = true;
     }
-    BackwardArgs ba{pr, st, active, n_active, i, 1, nullptr, nullptr};
+    const bool wide = P_alpha > 1 && i > 0;  // iteration 0 is an unconditional full step (ilqr.hh:70-73)
+    BackwardArgs ba{pr, st, active, n_active, i, wide ? PHASE_WIDE : PHASE_SEARCH, 1, nullptr, nullptr};
     {
       SpanGuard g(S, 0);
       launch_backward(S, ba);
     }
     S->stats.backward_problem_knots += int64_t(n_active) * N;
     S->stats.problem_iterations += n_active;
-    k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
-    S->launches += 2;
-    QCUDA(S, cudaStreamSynchronize(st_));
-    int n_search = S->h_counts[0];
+    ++S->launches;
     int n_next = 0;
-    int s = 0, rounds = 0;
-    while (n_search > 0) {
-      RolloutArgs ra{pr, st, listS[s], n_search, i, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr};
+    // forward_sim + cost + Armijo/convergence bookkeeping for the problems of `list` at their alpha[b]
+    auto rollout_list = [&](const int *list, int n) {
+      RolloutArgs ra{pr, st, list, n, i, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1};
       {
         SpanGuard g(S, 1);
-        k_rollout<<<blocks_for(n_search, 128), 128, 0, st_>>>(S->p, ra);
+        k_rollout<<<blocks_for(n, 128), 128, 0, st_>>>(S->p, ra);
       }
-      S->stats.rollout_problem_knots += int64_t(n_search) * N;
-      S->stats.problem_rollouts += n_search;
+      S->stats.rollout_problem_knots += int64_t(n) * N;
+      S->stats.problem_rollouts += n;
       ++S->launches;
       if (capture_debug) {
-        dim3 grid(blocks_for(n_search, 128), 32);
-        k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, listS[s], n_search, i, d_debug, debug_cap);
+        dim3 grid(blocks_for(n, 128), 32);
+        k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, list, n, i, d_debug, debug_cap);
         ++S->launches;
       }
-      k_compact<<<1, 1024, 0, st_>>>(listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur], S->d_counts);
+    };
+    if (!wide) {
+      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
       ++S->launches;
       QCUDA(S, cudaStreamSynchronize(st_));
-      n_search = S->h_counts[0];
-      n_next = S->h_counts[1];
-      s = 1 - s;
-      ++rounds;
-    }
-    if (rounds > 1) {  // rebuild the ordered active list from this iteration's list
+      int n_search = S->h_counts[0];
+      int s = 0, rounds = 0;
+      while (n_search > 0) {  // sequential backtracking: one more rollout for every problem that was rejected
+        rollout_list(listS[s], n_search);
+        k_compact<<<1, 1024, 0, st_>>>(listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur], S->d_counts);
+        ++S->launches;
+        QCUDA(S, cudaStreamSynchronize(st_));
+        n_search = S->h_counts[0];
+        n_next = S->h_counts[1];
+        s = 1 - s;
+        ++rounds;
+      }
+      if (rounds > 1) {  // rebuild the ordered active list from this iteration's list
+        k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
+        ++S->launches;
+        QCUDA(S, cudaStreamSynchronize(st_));
+        n_next = S->h_counts[1];
+      }
+    } else {
+      // parallel line search: P_alpha step sizes per problem and round as independent cost-only rollouts
+      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listF, S->d_counts, PHASE_WIDE, PHASE_SEARCH);
+      ++S->launches;
+      QCUDA(S, cudaStreamSynchronize(st_));
+      int n_wide = S->h_counts[0];
+      int s = 0;
+      while (n_wide > 0) {
+        RolloutArgs rw{pr, st, listS[s], n_wide, i, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha};
+        {
+          SpanGuard g(S, 1);
+          k_rollout<<<blocks_for(n_wide * P_alpha, 128), 128, 0, st_>>>(S->p, rw);
+        }
+        S->stats.rollout_problem_knots += int64_t(n_wide) * P_alpha * N;
+        k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B, S->wide_d.as<double>(), P_alpha);
+        k_compact<<<1, 1024, 0, st_>>>(listS[s], n_wide, st.phase, listS[1 - s], listF, S->d_counts, PHASE_WIDE, PHASE_SEARCH);
+        S->launches += 3;
+        QCUDA(S, cudaStreamSynchronize(st_));
+        n_wide = S->h_counts[0];
+        const int n_found = S->h_counts[1];
+        if (n_found > 0) rollout_list(listF, n_found);  // writes the accepted trajectory (same cost, accepted)
+        s = 1 - s;
+      }
       k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
       ++S->launches;
       QCUDA(S, cudaStreamSynchronize(st_));
@@ -459,7 +497,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
   cudaStreamSynchronize(S->stream);
   for (DeviceBuffer *b : {&S->buf1, &S->gk, &S->gK, &S->state_d, &S->state_i, &S->lists, &S->desired_soa,
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
-                          &S->debug_d, &S->misc})
+                          &S->debug_d, &S->misc, &S->wide_d})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
@@ -620,7 +658,7 @@ int qilqr_forward_sim_host(qilqr_solver_t *S, int B, int N, const double *curren
   QCUDA(S, cudaMemcpyAsync(S->misc.ptr, alpha, sizeof(double) * size_t(B), cudaMemcpyHostToDevice, st_));
   Problem pr{B, N, 1, nullptr, nullptr, nullptr, S->gk.as<double>(), S->gK.as<double>()};
   RolloutArgs ra{pr, SolveState{}, nullptr, B, 0, MODE_FORWARD, S->traj_soa.as<double>(), S->buf1.as<double>(),
-                 S->misc.as<double>(), nullptr};
+                 S->misc.as<double>(), nullptr, 1};
   k_rollout<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, ra);
   ++S->launches;
   unpack_traj(S, B, N, S->buf1.as<double>(), S->stage_a.as<double>());
@@ -669,7 +707,7 @@ int qilqr_backwards_pass_host(qilqr_solver_t *S, int B, int N, const double *des
   rc = upload_traj(S, S->stage_a, B, N, traj, S->traj_soa.as<double>());
   if (rc) return rc;
   Problem pr{B, N, Bd, nullptr, nullptr, S->desired_soa.as<double>(), S->gk.as<double>(), S->gK.as<double>()};
-  BackwardArgs ba{pr, SolveState{}, nullptr, B, 0, 0, S->traj_soa.as<double>(), S->misc.as<double>()};
+  BackwardArgs ba{pr, SolveState{}, nullptr, B, 0, PHASE_SEARCH, 0, S->traj_soa.as<double>(), S->misc.as<double>()};
   launch_backward(S, ba);
   ++S->launches;
   transpose_to_aos(S, S->gk.as<double>(), S->stage_c.as<double>(), B, N, 4);
@@ -724,7 +762,7 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
   const int *search = nullptr;
   int n_search = B, s = 0;
   while (n_search > 0) {
-    RolloutArgs ra{pr, st, search, n_search, 1, MODE_LINE_SEARCH, nullptr, nullptr, nullptr, nullptr};
+    RolloutArgs ra{pr, st, search, n_search, 1, MODE_LINE_SEARCH, nullptr, nullptr, nullptr, nullptr, 1};
     k_rollout<<<blocks_for(n_search, 128), 128, 0, st_>>>(S->p, ra);
     // phase: rejected problems keep PHASE_ACTIVE(0)... mark searching ones explicitly below
     k_compact<<<1, 1024, 0, st_>>>(search, n_search, st.phase, dummy, listS[s], S->d_counts);

@@ -23,8 +23,12 @@
 
 namespace qilqr {
 
-enum Phase : int { PHASE_ACTIVE = 0, PHASE_SEARCH = 1, PHASE_DONE = 2 };
-enum RolloutMode : int { MODE_FORWARD = 0, MODE_SOLVE = 1, MODE_LINE_SEARCH = 2 };
+// ACTIVE: needs a backward pass; SEARCH: needs a rollout at alpha[b]; WIDE: needs a round of parallel
+// step-size evaluations (num_parallel_alphas > 1); DONE: finished.
+enum Phase : int { PHASE_ACTIVE = 0, PHASE_SEARCH = 1, PHASE_DONE = 2, PHASE_WIDE = 3 };
+// FORWARD: plain forward_sim; SOLVE / LINE_SEARCH: with the bookkeeping of solve() / line_search();
+// WIDE: cost only, for step sizes alpha[b] * step_update^j, j = 0..palpha-1 (one thread per (problem, j)).
+enum RolloutMode : int { MODE_FORWARD = 0, MODE_SOLVE = 1, MODE_LINE_SEARCH = 2, MODE_WIDE = 3 };
 
 struct Problem {
   int B;   // batch (also the pitch of every SoA row)
@@ -104,12 +108,15 @@ struct RolloutArgs {
   const double *cur;
   double *out;
   const double *alpha_in;
-  double *cost_out;  // may be nullptr
+  double *cost_out;  // may be nullptr (MODE_WIDE: [palpha][B])
+  int palpha;        // MODE_WIDE: step sizes evaluated per problem
 };
 
 __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wide_j = (a.mode == MODE_WIDE) ? tid / a.n : 0;  // j-major so that a warp covers consecutive problems
+  const int t = (a.mode == MODE_WIDE) ? tid % a.n : tid;
+  if (tid >= a.n * ((a.mode == MODE_WIDE) ? a.palpha : 1)) return;
   const int b = a.list ? a.list[t] : t;
   const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
   const int bd = (Bd == 1) ? 0 : b;
@@ -118,6 +125,11 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceP
   double alpha;
   if (a.mode == MODE_FORWARD) {
     cur = a.cur; cand = a.out; alpha = a.alpha_in[b];
+  } else if (a.mode == MODE_WIDE) {
+    cur = a.st.sel[b] ? a.pr.buf1 : a.pr.buf0;
+    cand = nullptr;
+    alpha = a.st.alpha[b];
+    for (int j = 0; j < wide_j; ++j) alpha *= p.step_update;  // the same products as the sequential search
   } else {
     const int s = a.st.sel[b];
     cur = s ? a.pr.buf1 : a.pr.buf0;
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceP
       for (int s = 1; s < 12; ++s) Kd = fma(a.pr.gK[row_index(i, 12 * j + s, 48, B, b)], d[s], Kd);
       u[j] = (ubar[j] + alpha * kj) + Kd;
     }
-    store_point(cand, i, B, b, x, u);
+    if (a.mode != MODE_WIDE) store_point(cand, i, B, b, x, u);
     if (want_cost) {
       double xd[13], ud[4], dx[12], du[4];
       load_point(a.pr.desired, i, Bd, bd, xd, ud);
@@ -157,6 +169,10 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceP
 
   if (a.mode == MODE_FORWARD) {
     if (a.cost_out) a.cost_out[b] = cost;
+    return;
+  }
+  if (a.mode == MODE_WIDE) {
+    a.cost_out[size_t(wide_j) * B + b] = cost;
     return;
   }
   // ---- line_search / solve bookkeeping ----
@@ -303,6 +319,7 @@ struct BackwardArgs {
   const int *list;
   int n;
   int iter;
+  int search_phase;     // PHASE_SEARCH, or PHASE_WIDE when step sizes are evaluated in parallel
   int solve_mode;       // 1: solve() bookkeeping (exit A); 0: plain backwards_pass
   const double *traj;   // solve_mode == 0 only
   double *terms_out;    // solve_mode == 0 only: [B][2]
@@ -603,7 +620,46 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
   } else {
     st.alpha[b] = 1.0;
     st.ls_iter[b] = 0;
-    st.phase[b] = PHASE_SEARCH;
+    st.phase[b] = a.search_phase;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Parallel line search: after a MODE_WIDE round, pick the FIRST (largest) step size that passes the
+// Armijo test of ilqr.hh:182-188 -- exactly the one the sequential search would accept.  The accepted
+// problem moves to PHASE_SEARCH with alpha[b] set (the ordinary rollout then writes its trajectory and
+// accepts it); otherwise the next round starts palpha steps further down, or the search is exhausted.
+// `rollouts` and `ls_iter` count what the sequential search would have evaluated.
+// ---------------------------------------------------------------------------
+__global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveState st, const int *list, int n, int B,
+                               const double *wide_cost, int palpha) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int b = list ? list[t] : t;
+  const double cur_cost = st.cost[b], qutk = st.qutk[b], ktq = st.ktquuk[b];
+  double alpha = st.alpha[b];
+  const int ls0 = st.ls_iter[b];
+  int ls = ls0;
+  for (int j = 0; j < palpha; ++j) {
+    if (ls >= p.ls_max_iters) break;
+    const double cost = wide_cost[size_t(j) * B + b];
+    const double desired = p.desired_reduction_frac * (alpha * qutk + alpha * alpha * ktq / 2.0);
+    if (cost - cur_cost < desired) {
+      st.alpha[b] = alpha;
+      st.ls_iter[b] = ls;
+      st.rollouts[b] += ls - ls0;
+      st.phase[b] = PHASE_SEARCH;
+      return;
+    }
+    alpha *= p.step_update;
+    ++ls;
+  }
+  st.rollouts[b] += ls - ls0;
+  st.alpha[b] = alpha;
+  st.ls_iter[b] = ls;
+  if (ls >= p.ls_max_iters) {
+    st.status[b] = QILQR_STATUS_LINE_SEARCH_FAILED;
+    st.phase[b] = PHASE_DONE;
   }
 }
 
@@ -614,7 +670,8 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
 //   counts[0] = |out_search|, counts[1] = |out_active|   (mapped pinned host memory)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, const int *phase, int *out_search,
-                                                 int *out_active, volatile int *counts) {
+                                                 int *out_active, volatile int *counts, int phase_s = PHASE_SEARCH,
+                                                 int phase_a = PHASE_ACTIVE) {
   __shared__ int warp_s[32], warp_a[32];
   __shared__ int base_s, base_a;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -627,8 +684,8 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
       b = list_in ? list_in[idx] : idx;
       ph = phase[b];
     }
-    const unsigned ms = __ballot_sync(0xffffffffu, ph == PHASE_SEARCH);
-    const unsigned ma = __ballot_sync(0xffffffffu, ph == PHASE_ACTIVE);
+    const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
+    const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
     if (lane == 0) { warp_s[wid] = __popc(ms); warp_a[wid] = __popc(ma); }
     __syncthreads();
     if (wid == 0) {
@@ -644,8 +701,8 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
     __syncthreads();
     const int off_s = base_s + (wid ? warp_s[wid - 1] : 0) + __popc(ms & ((1u << lane) - 1));
     const int off_a = base_a + (wid ? warp_a[wid - 1] : 0) + __popc(ma & ((1u << lane) - 1));
-    if (ph == PHASE_SEARCH) out_search[off_s] = b;
-    if (ph == PHASE_ACTIVE) out_active[off_a] = b;
+    if (ph == phase_s) out_search[off_s] = b;
+    if (ph == phase_a) out_active[off_a] = b;
     __syncthreads();
     if (tid == 0) { base_s += warp_s[31]; base_a += warp_a[31]; }
     __syncthreads();

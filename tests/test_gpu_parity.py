@@ -379,3 +379,94 @@ def test_device_resident_path_matches_host_path():
     assert stats["problem_iterations"] == int(host["results"]["backward_passes"].sum())
     assert stats["problem_rollouts"] == int(host["results"]["rollouts"].sum())
     assert stats["kernel_launches"] > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# parallel line search (north star item 4) and the long-horizon config (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------
+def test_parallel_alphas_equal_sequential_search(O):
+    """Evaluating P step sizes per round as parallel rollouts must accept exactly the step the
+    sequential backtracking accepts: same trajectories (bit for bit vs the sequential GPU path),
+    same counts as the oracle.  The default problem backtracks once (alpha = 0.5 at iteration 4)."""
+    import dataclasses
+    from quadrotorilqr_b200 import ConvergenceCriteria, ILQROptions, LineSearchParams, problems
+
+    model = problems.default_model()
+    desired = problems.default_desired_trajectory()
+    seq = make_solver(model, problems.default_options(False)).solve(desired[None], desired, want_gains=True, hist_cap=100)
+    for P in (2, 8):
+        opts = dataclasses.replace(problems.default_options(False), num_parallel_alphas=P)
+        par = make_solver(model, opts).solve(desired[None], desired, want_gains=True, hist_cap=100)
+        assert np.array_equal(par["traj"], seq["traj"]) and np.array_equal(par["K"], seq["K"])
+        assert np.array_equal(par["results"], seq["results"])
+        assert np.array_equal(par["cost_history"], seq["cost_history"])
+    # forced exhaustion and multi-round backtracking (line search limit 5, P = 2 -> 3 rounds)
+    model = problems.hover_model()
+    opts = ILQROptions(LineSearchParams(0.5, 4.0, 5), ConvergenceCriteria(1e-14, 0.0, 20.0), num_parallel_alphas=2)
+    s = make_solver(model, opts)
+    cfg = oracle_config(O, model, opts)
+    desired, initial = hover_batch(s, 9, 10, seed=2)
+    r, o = check_solve_against_oracle(O, s, cfg, desired, initial)
+    assert np.any(r["results"]["status"] == 4)
+    # hover batch with P = 4
+    opts = dataclasses.replace(problems.default_options(False), num_parallel_alphas=4)
+    s = make_solver(model, opts)
+    cfg = oracle_config(O, model, opts)
+    desired, initial = hover_batch(s, 40, 40, seed=8)
+    check_solve_against_oracle(O, s, cfg, desired, initial)
+
+
+def test_long_horizon_figure_eight(O):
+    """BASELINE config 4 at a size the oracle finishes in seconds: N = 1000, dt = 0.02, figure-eight
+    tracking, 8 parallel alphas, symmetrised V_xx in BOTH oracle and GPU (the unsymmetrised reference
+    recursion diverges at this horizon -- SURVEY fact 5).  Tolerance: iteration counts / flags identical;
+    trajectories within 1e-7 relative (rounding differences are amplified along 1000 knots)."""
+    import dataclasses
+    from quadrotorilqr_b200 import problems
+
+    N, dt = 1000, 0.02
+    model = dict(problems.hover_model(), dt_s=dt)
+    opts = dataclasses.replace(problems.default_options(False), symmetrize_vxx=True, num_parallel_alphas=8)
+    s = make_solver(model, opts)
+    cfg = oracle_config(O, model, opts)
+    desired = problems.figure_eight_desired(N, dt)
+    rng = np.random.default_rng(4)
+    B = 3
+    x0 = np.tile(desired[0, 1:14], (B, 1))
+    x0[:, 0:3] += rng.uniform(-0.3, 0.3, (B, 3))
+    seedtraj = problems.constant_state_trajectory(x0, N, dt, desired[0, 14:18])
+    initial = s.forward_sim(seedtraj, np.zeros((B, N, 4)), np.zeros((B, N, 48)))
+    r = s.solve(initial, desired, hist_cap=100)
+    o = O.solve_batch(cfg, desired, initial, hist_cap=100)
+    assert np.array_equal(r["results"]["status"], o["status"])
+    assert np.array_equal(r["results"]["backward_passes"], o["backward_passes"])
+    assert np.array_equal(r["results"]["rollouts"], o["rollouts"])
+    assert np.all(np.isin(o["status"], [1, 2])) and o["backward_passes"].max() < 30
+    for b in range(B):
+        assert_close(r["traj"][b], o["traj"][b], rtol=1e-7, what="long-horizon traj")
+        assert_close(r["cost_history"][b], o["cost_history"][b], rtol=1e-9, what="long-horizon cost history")
+
+
+def test_quad_and_thread_backward_kernels_agree(monkeypatch):
+    """The 4-lanes-per-problem kernel and the one-thread-per-problem kernel implement the same
+    recursion; they must agree to rounding on the same inputs."""
+    from quadrotorilqr_b200 import problems
+
+    model, opts = problems.hover_model(), problems.default_options(False)
+    s_quad = make_solver(model, opts)
+    desired, initial = hover_batch(s_quad, 21, 40, seed=12)
+    monkeypatch.setenv("QILQR_BACKWARD", "t1")
+    s_thread = make_solver(model, opts)
+    monkeypatch.delenv("QILQR_BACKWARD")
+    kq, Kq, aq, cq = s_quad.backwards_pass(initial, desired)
+    kt, Kt, at, ct = s_thread.backwards_pass(initial, desired)
+    assert_close(Kq, Kt, rtol=1e-11, what="K")
+    assert_close(kq, kt, rtol=1e-11, what="k")
+    assert_close(aq, at, rtol=1e-11, what="QuTk")
+    assert_close(cq, ct, rtol=1e-11, what="kTQuuk")
+    for kpp in ("1", "2"):
+        monkeypatch.setenv("QILQR_KPP", kpp)
+        s_k = make_solver(model, opts)
+        monkeypatch.delenv("QILQR_KPP")
+        k2, K2, a2, c2 = s_k.backwards_pass(initial, desired)
+        assert np.array_equal(K2, Kq) and np.array_equal(k2, kq)  # same arithmetic, different staging
