@@ -196,6 +196,22 @@ int qilqr_rollout_constant_control_device(qilqr_solver_t *solver, int batch, int
                                           const double *d_x0_soa, const double *u_const /*host[4]*/,
                                           double *d_traj_soa);
 
+/* Receding-horizon MPC on top of solve(initial_traj) (ilqr.hh:53-55; BASELINE config 5), all on the device.
+ * One closed-loop step = solve from the warm start, apply the first control to the plant
+ * (QuadrotorModel::discrete_dynamics, optionally plus an additive body-velocity disturbance
+ * d_disturbance[6][batch]), shift the solution one knot (last knot duplicated) and put the new plant
+ * state in knot 0.  d_plant_state [13][batch] and d_traj_inout are updated in place.
+ * qilqr_mpc_run_device repeats that `steps` times; d_state_log [steps][13][batch] and
+ * d_control_log [steps][4][batch] (either may be NULL) receive the plant state after and the control
+ * applied at every step; totals[0..3] (host, may be NULL) = sum of backward passes, sum of rollouts,
+ * number of re-solves that did not converge (status 3 or 4), number of re-solves. */
+int qilqr_mpc_advance_device(qilqr_solver_t *solver, int batch, int n_knots, double *d_traj_inout,
+                             double *d_plant_state, const double *d_disturbance, double *d_applied_u);
+int qilqr_mpc_run_device(qilqr_solver_t *solver, int steps, int batch, int n_knots, const double *d_desired,
+                         int desired_count, double *d_traj_inout, double *d_plant_state,
+                         const double *d_disturbance, double *d_state_log, double *d_control_log,
+                         int64_t *totals);
+
 /* Aggregate counters of the last qilqr_solve_* call. */
 typedef struct {
   int64_t solver_iterations;   /* outer iterations issued (max over problems) */

@@ -562,6 +562,62 @@ int qilqr_rollout_constant_control_device(qilqr_solver_t *S, int batch, int n_kn
   return QILQR_OK;
 }
 
+int qilqr_mpc_advance_device(qilqr_solver_t *S, int B, int N, double *d_traj, double *d_plant, const double *d_dist,
+                             double *d_applied_u) {
+  if (!S || !d_traj || !d_plant || B <= 0 || N <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  k_mpc_advance<<<blocks_for(B, 128), 128, 0, S->stream>>>(S->p, d_traj, d_plant, d_dist, d_applied_u, B, N);
+  ++S->launches;
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const double *d_desired, int Bd, double *d_traj,
+                         double *d_plant, const double *d_dist, double *d_state_log, double *d_control_log,
+                         int64_t *totals) {
+  if (!S || !d_desired || !d_traj || !d_plant || steps < 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QCUDA(S, cudaSetDevice(S->device));
+  QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
+  std::vector<qilqr_result_t> res(totals ? B : 0);
+  int64_t acc[4] = {0, 0, 0, 0};
+  qilqr_solve_stats_t total_stats{};
+  for (int t = 0; t < steps; ++t) {
+    int rc = solve_core(S, B, N, d_desired, Bd, d_traj, nullptr, nullptr, nullptr, 0,
+                        S->results_d.as<qilqr_result_t>(), nullptr, 0);
+    if (rc) return rc;
+    total_stats.solver_iterations += S->stats.solver_iterations;
+    total_stats.problem_iterations += S->stats.problem_iterations;
+    total_stats.problem_rollouts += S->stats.problem_rollouts;
+    total_stats.kernel_launches += S->stats.kernel_launches + 1;
+    total_stats.backward_ms += S->stats.backward_ms;
+    total_stats.rollout_ms += S->stats.rollout_ms;
+    total_stats.backward_problem_knots += S->stats.backward_problem_knots;
+    total_stats.rollout_problem_knots += S->stats.rollout_problem_knots;
+    double *u_log = d_control_log ? d_control_log + size_t(t) * 4 * B : nullptr;
+    k_mpc_advance<<<blocks_for(B, 128), 128, 0, S->stream>>>(S->p, d_traj, d_plant, d_dist, u_log, B, N);
+    ++S->launches;
+    if (d_state_log)
+      QCUDA(S, cudaMemcpyAsync(d_state_log + size_t(t) * 13 * B, d_plant, sizeof(double) * 13 * size_t(B),
+                               cudaMemcpyDeviceToDevice, S->stream));
+    if (totals) {
+      QCUDA(S, cudaMemcpyAsync(res.data(), S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B),
+                               cudaMemcpyDeviceToHost, S->stream));
+      QCUDA(S, cudaStreamSynchronize(S->stream));
+      for (int b = 0; b < B; ++b) {
+        acc[0] += res[b].backward_passes;
+        acc[1] += res[b].rollouts;
+        acc[2] += (res[b].status == QILQR_STATUS_MAX_ITERS || res[b].status == QILQR_STATUS_LINE_SEARCH_FAILED);
+      }
+      acc[3] += B;
+    }
+  }
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  QCUDA(S, cudaGetLastError());
+  S->stats = total_stats;
+  if (totals) for (int i = 0; i < 4; ++i) totals[i] = acc[i];
+  return QILQR_OK;
+}
+
 // ---- host-buffer API -----------------------------------------------------------
 int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *initial,
                      double *out_traj, double *out_k, double *out_K, double *cost_hist, int hist_cap,

@@ -845,6 +845,37 @@ __global__ void k_api_cost(const __grid_constant__ DeviceParams p, int B, const 
   if (C_xu) for (int e = 0; e < 48; ++e) C_xu[size_t(b) * 48 + e] = 0.0;
 }
 
+// Receding-horizon step (BASELINE config 5): apply the first control of the solution to the plant
+// (one discrete_dynamics step, optionally with an additive body-velocity disturbance), then shift the
+// solution by one knot as the warm start of the next solve (last knot duplicated) and set its first
+// state to the new plant state.  solve() uses initial_traj.front().state as x0 (ilqr.hh:156).
+__global__ void __launch_bounds__(128)
+k_mpc_advance(const __grid_constant__ DeviceParams p, double *traj, double *plant /*[13][B]*/,
+              const double *disturbance /*[6][B] or nullptr*/, double *applied_u /*[4][B] or nullptr*/, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[13], u[4];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) x[c] = plant[size_t(c) * B + b];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) u[c] = traj[row_index(0, 13 + c, 17, B, b)];
+  discrete_step(p, x, x + 3, x + 7, u);
+  if (disturbance) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) x[7 + c] += disturbance[size_t(c) * B + b];
+  }
+#pragma unroll
+  for (int c = 0; c < 13; ++c) plant[size_t(c) * B + b] = x[c];
+  if (applied_u) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) applied_u[size_t(c) * B + b] = u[c];
+  }
+  for (int i = 0; i + 1 < N; ++i)
+    for (int c = 0; c < 17; ++c) traj[row_index(i, c, 17, B, b)] = traj[row_index(i + 1, c, 17, B, b)];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) traj[row_index(0, c, 17, B, b)] = x[c];
+}
+
 // Open-loop rollout under a constant control from per-problem initial states.
 __global__ void __launch_bounds__(128)
 k_rollout_constant(const __grid_constant__ DeviceParams p, const double *x0 /*[13][B]*/, double u0, double u1,

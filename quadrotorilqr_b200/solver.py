@@ -196,6 +196,24 @@ class BatchILQR:
         self._check(_capi.lib().qilqr_rollout_constant_control_device(self._h, C.c_int(B), C.c_int(N),
                                                                       _ptr(x0_soa), _ptr(u), _ptr(traj_soa)))
 
+    def mpc_advance_device(self, traj_soa, plant_soa, disturbance=None, applied_u=None):
+        N, _, B = traj_soa.shape
+        self._check(_capi.lib().qilqr_mpc_advance_device(self._h, C.c_int(B), C.c_int(N), _ptr(traj_soa),
+                                                         _ptr(plant_soa), _ptr(disturbance), _ptr(applied_u)))
+
+    def mpc_run_device(self, steps, traj_soa, desired_soa, plant_soa, disturbance=None, state_log=None,
+                       control_log=None):
+        """Receding-horizon loop on the device (BASELINE config 5): `steps` x (solve from the warm start,
+        apply u_0 to the plant, shift).  Returns dict(backward_passes, rollouts, not_converged, resolves)."""
+        N, _, B = traj_soa.shape
+        Bd = int(desired_soa.shape[2])
+        totals = (C.c_int64 * 4)()
+        self._check(_capi.lib().qilqr_mpc_run_device(self._h, C.c_int(int(steps)), C.c_int(B), C.c_int(N),
+                                                     _ptr(desired_soa), C.c_int(Bd), _ptr(traj_soa), _ptr(plant_soa),
+                                                     _ptr(disturbance), _ptr(state_log), _ptr(control_log), totals))
+        return dict(backward_passes=int(totals[0]), rollouts=int(totals[1]), not_converged=int(totals[2]),
+                    resolves=int(totals[3]))
+
     # ---- ILQR::forward_sim / cost_trajectory / backwards_pass / line_search ------------------
     def forward_sim(self, current, k, K, alpha=1.0):
         current = _f64(current)
