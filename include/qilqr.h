@@ -232,6 +232,10 @@ int qilqr_set_profiling(qilqr_solver_t *solver, int enabled);
  * in TFLOP/s (2 flops per DFMA), from a register-resident DFMA kernel timed with CUDA events. */
 int qilqr_measure_fp64_peak(int device, double *tflops);
 
+/* The QuadrotorModel constructor's validity test (quadrotor_model.cc:20-24): QILQR_OK, or
+ * QILQR_ERR_INERTIA_NOT_PD when the inertia is not symmetric positive definite.  Host only. */
+int qilqr_check_model(const qilqr_model_t *model);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "qilqr_cost_host", "qilqr_solve_device", "qilqr_pack_trajectory_device",
     "qilqr_unpack_trajectory_device", "qilqr_rollout_constant_control_device",
     "qilqr_last_solve_stats", "qilqr_set_profiling", "qilqr_measure_fp64_peak",
-    "qilqr_mpc_advance_device", "qilqr_mpc_run_device",
+    "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
 ]
 
 

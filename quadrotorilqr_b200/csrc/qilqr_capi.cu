@@ -991,6 +991,12 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, doubl
 }
 }  // namespace
 
+int qilqr_check_model(const qilqr_model_t *model) {
+  if (!model) return QILQR_ERR_INVALID_ARGUMENT;
+  double L[9];
+  return factor_inertia(model->inertia, L) ? QILQR_OK : QILQR_ERR_INERTIA_NOT_PD;
+}
+
 int qilqr_measure_fp64_peak(int device, double *tflops) {
   if (!tflops) return QILQR_ERR_INVALID_ARGUMENT;
   if (cudaSetDevice(device) != cudaSuccess) return QILQR_ERR_NO_DEVICE;
