@@ -1,0 +1,43 @@
+"""Drop-in for the reference's pybind module ``src.quadrotor_ilqr_binding``
+(``src/quadrotor_ilqr_binding.cc:20-49``): the same class name, constructor arguments and
+``solve`` signature, taking and returning the same protobuf messages -- backed by the CUDA library.
+
+    from quadrotorilqr_b200.quadrotor_ilqr_binding import QuadrotorILQR
+    ilqr = QuadrotorILQR(mass_kg, inertia, arm_length_m, torque_to_thrust_ratio_m, g_mpss, Q, R,
+                         desired_traj, dt_s, options)          # protos as in quadrotor_ilqr.py:294-305
+    opt_traj, debug = ilqr.solve(initial_traj)                   # (QuadrotorTrajectory, QuadrotorILQRDebug)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi, protos
+from .solver import BatchILQR
+
+
+class QuadrotorILQR:
+    def __init__(self, mass_kg, inertia, arm_length_m, torque_to_thrust_ratio_m, g_mpss, Q, R, desired_traj, dt_s,
+                 options, device: int = 0):
+        self._options = protos.options_from_proto(options)
+        self._desired = protos.trajectory_from_proto(desired_traj)
+        self._solver = BatchILQR(mass_kg, np.asarray(inertia, dtype=np.float64), arm_length_m,
+                                 torque_to_thrust_ratio_m, g_mpss, np.asarray(Q, dtype=np.float64),
+                                 np.asarray(R, dtype=np.float64), dt_s, self._options, device=device)
+
+    def solve(self, initial_traj):
+        init = protos.trajectory_from_proto(initial_traj)
+        n = init.shape[0]
+        if n > self._desired.shape[0]:
+            raise IndexError("vector::_M_range_check")  # std::out_of_range, cost.hh:39-40
+        if n == 0:
+            raise ValueError("empty trajectory")  # undefined behaviour in the reference (ilqr.hh:156)
+        r = self._solver.solve(init[None], self._desired[:n],
+                               hist_cap=int(np.ceil(self._options.convergence_criteria.max_iters)) + 1,
+                               want_debug=self._options.populate_debug)
+        res = r["results"][0]
+        if res["status"] == _capi.STATUS_LINE_SEARCH_FAILED:  # std::runtime_error, ilqr.hh:191-193
+            raise RuntimeError("Reached maximum number of line search iterations, "
+                               f"{self._options.line_search_params.max_iters}\n")
+        nd = int(res["num_debug"]) if self._options.populate_debug else 0
+        debug = protos.debug_to_proto(r["debug"][0][:nd] if nd else [], r["cost_history"][0][:nd] if nd else [])
+        return protos.trajectory_to_proto(r["traj"][0]), debug
