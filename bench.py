@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-serial", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2,
+    ap.add_argument("--pipeline", type=int, default=4,
                     help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
     args = ap.parse_args()
 
@@ -205,7 +205,6 @@ def main():
     def make_solver():
         s_ = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
                        m["Q"], m["R"], m["dt_s"], opts, device=local_rank)
-        s_.set_profiling(True)
         return s_
 
     # P solver handles = a P-deep software pipeline of batches: each handle is driven by its own host
@@ -285,23 +284,27 @@ def main():
     launches = sum(s_.kernel_launch_count for s_ in solvers) - launches0
     clocks = sampler.stop()
     dev_ms = max(ev0[j].elapsed_time(ev1[j]) for j in range(P))
-    bwd_ms, roll_ms = tot["backward_ms"], tot["rollout_ms"]
-    bwd_knots, roll_knots = tot["backward_problem_knots"], tot["rollout_problem_knots"]
     prob_iters, prob_rollouts, solver_iters = tot["problem_iterations"], tot["problem_rollouts"], tot["solver_iterations"]
     res = np.frombuffer(res_dev[0].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     converged = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
     ls_failed = int(np.sum(res["status"] == 4))
     max_iter_hit = int(np.sum(res["status"] == 3))
 
-    # one batch at a time on one handle (no pipelining), for reference
-    serial_ms = None
-    if P > 1 and not args.no_serial:
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(2):
-            device_step(0)
-        torch.cuda.synchronize()
-        serial_ms = 1e3 * (time.perf_counter() - t0) / 2
+    # One batch at a time on one handle (no pipelining): the latency of a single batch, and the place
+    # where the kernels are timed ALONE with CUDA events on the solver's stream (inside the pipelined
+    # region above kernels of different handles overlap, so per-kernel durations are not separable).
+    barrier()
+    solvers[0].set_profiling(True)
+    ser = {k_: 0 for k_ in STAT_KEYS}
+    n_serial = 3
+    t0 = time.perf_counter()
+    for _ in range(n_serial):
+        device_step(0, ser)
+    torch.cuda.synchronize()
+    serial_ms = 1e3 * (time.perf_counter() - t0) / n_serial
+    solvers[0].set_profiling(False)
+    bwd_ms, roll_ms = ser["backward_ms"], ser["rollout_ms"]
+    bwd_knots, roll_knots = ser["backward_problem_knots"], ser["rollout_problem_knots"]
 
     # ---- `e2e`: host buffers through qilqr_solve_host ------------------------------------------
     e2e = None
@@ -375,7 +378,7 @@ def main():
     # algorithmic HBM bytes of the backward kernel: read 17 doubles (+17 desired if per-problem), write 52
     bwd_bytes = bwd_knots * (17 + 52) * 8.0
     roofline = {
-        "kernel": "k_backward (ILQR::backwards_pass, linearisation fused into the Riccati sweep)",
+        "kernel": "backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)",
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": (achieved / peak.value) if (achieved and peak.value) else None,
         "peak_source": "measured in this run: register-resident DFMA kernel (qilqr_measure_fp64_peak); "
@@ -383,12 +386,12 @@ def main():
         "flops_per_problem_knot": F_BWD,
         "flops_definition": "dense as-written reference arithmetic counted by the oracle's FLOP-counting scalar",
         "traffic": None,
-        "share_of_step": bwd_ms / (ms_per_step * args.steps) if ms_per_step else None,
+        "share_of_step": bwd_ms / (serial_ms * n_serial),
+        "timed": f"CUDA events around every launch of {n_serial} un-pipelined steps run right after the timed region",
         "hbm": {"achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "peak": hbm_peak,
                 "unit": "GB/s", "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak) if bwd_ms > 0 else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "of fallback"},
-        "rollout_kernel": {"achieved": roll_achieved, "unit": "TFLOP/s", "share_of_step":
-                           roll_ms / (ms_per_step * args.steps) if ms_per_step else None},
+        "rollout_kernel": {"achieved": roll_achieved, "unit": "TFLOP/s", "share_of_step": roll_ms / (serial_ms * n_serial)},
     }
 
     line = {

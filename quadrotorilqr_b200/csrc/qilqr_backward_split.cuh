@@ -1,0 +1,154 @@
+// =============================================================================
+// qilqr_backward_split.cuh -- ILQR::backwards_pass (ilqr.hh:97-147) as two kernels:
+//
+//   k_linearise   one thread per (problem, knot): all knots of all problems are linearised in
+//                 parallel (dynamics blocks, cost gradient, pose block of the Gauss-Newton Hessian)
+//                 into 100-double records, stored as tiles  rec[tile of 8 problems][knot][elem][8]
+//   k_riccati_g4  one warp per tile of 8 problems (4 lanes each): walks the horizon backwards; the
+//                 next knot's 6.4 kB record tile is fetched by a TMA bulk copy
+//                 (cp.async.bulk + mbarrier, double-buffered) while the current knot's Riccati step
+//                 (qilqr_riccati_step.cuh) runs on registers / shared memory.
+//
+// Compared with the fused kernel (qilqr_backward_g4.cuh) this removes the Lie-group code and the
+// per-problem record storage from the sequential kernel (smaller code, less shared memory per warp
+// -> more resident warps), makes the scalar linearisation fully parallel, and costs one round trip
+// of the records through HBM (800 B per problem-knot).
+// =============================================================================
+#pragma once
+#include <cstdint>
+
+#include "qilqr_backward_g4.cuh"
+
+namespace qilqr {
+namespace g4 {
+
+constexpr int RECT = 100;             // record elements actually used (REC = 101 has one pad element)
+constexpr int TILE = RECT * 8;        // doubles per (tile, knot): 6400 B, a multiple of 16
+constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
+constexpr int SPLIT_SMEM_DOUBLES = 2 * TILE + 8 * XS + 36 * 8 + 2;
+
+QD uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+QD void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+QD void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+QD void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+QD void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+}  // namespace g4
+
+// One thread per (slot, knot); slots are padded to whole tiles of 8 (padding replicates the last
+// problem so that every record is finite).  Consecutive threads = consecutive slots.
+__global__ void __launch_bounds__(128) k_linearise(const __grid_constant__ DeviceParams p,
+                                                   const __grid_constant__ BackwardArgs a, double *rec_g) {
+  using namespace g4;
+  const int n8 = (a.n + 7) & ~7;
+  const size_t id = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int N = a.pr.N;
+  if (id >= size_t(n8) * N) return;
+  const int t = int(id % n8), i = int(id / n8);
+  const int tt = t < a.n ? t : a.n - 1;
+  const int b = a.list ? a.list[tt] : tt;
+  const int B = a.pr.B, Bd = a.pr.Bd;
+  const int bd = (Bd == 1) ? 0 : b;
+  const double *traj = a.solve_mode ? (a.st.sel[b] ? a.pr.buf1 : a.pr.buf0) : a.traj;
+  double x[13], u[4], xd[13], ud[4];
+  load_point(traj, i, B, b, x, u);
+  load_point(a.pr.desired, i, Bd, bd, xd, ud);
+  double *dst = rec_g + (size_t(t >> 3) * N + i) * TILE + (t & 7);
+  linearise_to_record<8>(p, x, u, xd, ud, dst);
+}
+
+__global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ DeviceParams p,
+                                                   const __grid_constant__ BackwardArgs a, const double *rec_g) {
+  using namespace g4;
+  extern __shared__ __align__(128) double smem[];
+  const int lane = threadIdx.x, c = lane & 3, q = lane >> 2;
+  const int tile = blockIdx.x;
+  const int t = tile * 8 + q;
+  const bool valid = t < a.n;
+  const int tt = valid ? t : a.n - 1;
+  const int b = a.list ? a.list[tt] : tt;
+  const int B = a.pr.B, N = a.pr.N;
+  double *bufs = smem;
+  double *xch = smem + 2 * TILE + q * XS;
+  double *s2Qvv = smem + 2 * TILE + 8 * XS;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36 * 8);
+  for (int e = lane; e < 36; e += 32) s2Qvv[e * 8] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
+  if (lane == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const double *src = rec_g + size_t(tile) * N * TILE;
+  constexpr uint32_t kBytes = TILE * sizeof(double);
+  if (lane == 0) {
+    mbar_expect_tx(&mbar[0], kBytes);
+    bulk_copy_g2s(bufs, src + size_t(N - 1) * TILE, kBytes, &mbar[0]);
+  }
+  uint32_t phase0 = 0, phase1 = 0;
+
+  double V0[9], V1[9], V2[9], V3[9], vx[12];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) V0[e] = V1[e] = V2[e] = V3[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 12; ++e) vx[e] = 0.0;
+  double QuTk = 0.0, kTQuuk = 0.0;
+
+#pragma unroll 1
+  for (int i = N - 1; i >= 0; --i) {
+    const int s = (N - 1 - i) & 1;
+    if (i > 0 && lane == 0) {
+      // the other buffer was last read (generic proxy) during the previous knot's step, which every
+      // lane has left through the step's final __syncwarp: order those reads before the async write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[s ^ 1], kBytes);
+      bulk_copy_g2s(bufs + (s ^ 1) * TILE, src + size_t(i - 1) * TILE, kBytes, &mbar[s ^ 1]);
+    }
+    if (s == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+    else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+    riccati_step<8>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, QuTk, kTQuuk);
+  }
+
+  if (!valid || c != 0) return;
+  if (!a.solve_mode) {
+    a.terms_out[2 * size_t(b)] = QuTk;
+    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
+    return;
+  }
+  const SolveState &st = a.st;
+  st.qutk[b] = QuTk;
+  st.ktquuk[b] = kTQuuk;
+  st.bwd[b] += 1;
+  const double cost = st.cost[b];
+  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
+  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
+    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
+    st.phase[b] = PHASE_DONE;
+  } else {
+    st.alpha[b] = 1.0;
+    st.ls_iter[b] = 0;
+    st.phase[b] = a.search_phase;
+  }
+}
+
+}  // namespace qilqr

@@ -17,6 +17,7 @@
 #include "qilqr_api_kernels.cuh"
 #include "qilqr_kernels.cuh"
 #include "qilqr_backward_g4.cuh"
+#include "qilqr_backward_split.cuh"
 
 using namespace qilqr;
 
@@ -57,6 +58,7 @@ struct qilqr_solver {
   cudaStream_t stream_hi = nullptr;  // the latency-bound tail of a solve (few problems left), highest priority
   cudaStream_t cur = nullptr;        // the one solve_core is currently launching on
   cudaEvent_t ev_switch = nullptr;
+  int lists_B = 0;                   // batch the list buffer is laid out for
   int hi_threshold = 2048;           // switch to stream_hi when at most this many problems are active
   std::string last_error;
   int64_t launches = 0;
@@ -64,12 +66,13 @@ struct qilqr_solver {
   bool profiling = false;
   bool q_block_diagonal = true;  // Q = blkdiag(Q_pp, Q_vv): the 4-lanes-per-problem backward kernel applies
   int g4_kpp = 4;                // knots linearised per phase by the quad kernel (1, 2 or 4)
+  bool split_backward = true;    // linearise kernel + TMA-fed Riccati kernel (default) vs the fused quad kernel
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
 
   // workspace
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
-      hist_d, debug_d, misc, wide_d;
+      hist_d, debug_d, misc, wide_d, rec_d;
   int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
   int *d_counts = nullptr;
 };
@@ -193,11 +196,28 @@ SolveState make_state(qilqr_solver *S, int B, double *hist, int hist_cap) {
 int ensure_state(qilqr_solver *S, int B) {
   QCUDA(S, S->state_d.ensure(sizeof(double) * StateLayout::kDoubles * size_t(B)));
   QCUDA(S, S->state_i.ensure(sizeof(int) * StateLayout::kInts * size_t(B)));
-  QCUDA(S, S->lists.ensure(sizeof(int) * 5 * size_t(B)));
+  QCUDA(S, S->lists.ensure(sizeof(int) * (5 * size_t(B) + 2 * (size_t(B) / 1024 + 2))));
+  S->lists_B = B;
   return QILQR_OK;
 }
 
 inline unsigned blocks_for(int n, int per) { return unsigned((n + per - 1) / per); }
+
+// Ordered compaction of `list` (n entries) by phase into two lists; the two lengths land in S->h_counts
+// after the next synchronisation of S->cur.
+void launch_compact(qilqr_solver *S, const int *list, int n, const int *phase, int *out_s, int *out_a,
+                    int phase_s = PHASE_SEARCH, int phase_a = PHASE_ACTIVE) {
+  if (n <= 4096) {
+    k_compact<<<1, 1024, 0, S->cur>>>(list, n, phase, out_s, out_a, S->d_counts, phase_s, phase_a);
+    ++S->launches;
+    return;
+  }
+  const int chunks = (n + 1023) / 1024;
+  int *chunk_counts = S->lists.as<int>() + 5 * size_t(S->lists_B);
+  k_compact_count<<<chunks, 1024, 0, S->cur>>>(list, n, phase, chunk_counts, phase_s, phase_a);
+  k_compact_scatter<<<chunks, 1024, 0, S->cur>>>(list, n, phase, chunk_counts, out_s, out_a, S->d_counts, phase_s, phase_a);
+  S->launches += 2;
+}
 
 template <int KPP>
 void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
@@ -213,8 +233,27 @@ void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
 }
 // ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
 // coupling, one-thread-per-problem kernel otherwise.
+int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
+  const int n8 = (ba.n + 7) & ~7;
+  const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * g4::TILE / 8;
+  if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
+  const size_t smem = sizeof(double) * g4::SPLIT_SMEM_DOUBLES;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_riccati_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_riccati_g4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const size_t threads = size_t(n8) * ba.pr.N;
+  k_linearise<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  k_riccati_g4<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  ++S->launches;
+  return QILQR_OK;
+}
 void launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
-  if (!S->q_block_diagonal) {
+  if (S->q_block_diagonal && S->split_backward) {
+    launch_split(S, ba);
+  } else if (!S->q_block_diagonal) {
     k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->cur>>>(S->p, ba);
   } else if (S->g4_kpp == 1) {
     launch_g4<1>(S, ba);
@@ -302,15 +341,13 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       }
     };
     if (!wide) {
-      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
-      ++S->launches;
+      launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
       QCUDA(S, cudaStreamSynchronize(st_));
       int n_search = S->h_counts[0];
       int s = 0, rounds = 0;
       while (n_search > 0) {  // sequential backtracking: one more rollout for every problem that was rejected
         rollout_list(listS[s], n_search);
-        k_compact<<<1, 1024, 0, st_>>>(listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur], S->d_counts);
-        ++S->launches;
+        launch_compact(S, listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur]);
         QCUDA(S, cudaStreamSynchronize(st_));
         n_search = S->h_counts[0];
         n_next = S->h_counts[1];
@@ -318,15 +355,13 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         ++rounds;
       }
       if (rounds > 1) {  // rebuild the ordered active list from this iteration's list
-        k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
-        ++S->launches;
+        launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
         QCUDA(S, cudaStreamSynchronize(st_));
         n_next = S->h_counts[1];
       }
     } else {
       // parallel line search: P_alpha step sizes per problem and round as independent cost-only rollouts
-      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listF, S->d_counts, PHASE_WIDE, PHASE_SEARCH);
-      ++S->launches;
+      launch_compact(S, active, n_active, st.phase, listS[0], listF, PHASE_WIDE, PHASE_SEARCH);
       QCUDA(S, cudaStreamSynchronize(st_));
       int n_wide = S->h_counts[0];
       int s = 0;
@@ -338,16 +373,15 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         }
         S->stats.rollout_problem_knots += int64_t(n_wide) * P_alpha * N;
         k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B, S->wide_d.as<double>(), P_alpha);
-        k_compact<<<1, 1024, 0, st_>>>(listS[s], n_wide, st.phase, listS[1 - s], listF, S->d_counts, PHASE_WIDE, PHASE_SEARCH);
-        S->launches += 3;
+        launch_compact(S, listS[s], n_wide, st.phase, listS[1 - s], listF, PHASE_WIDE, PHASE_SEARCH);
+        S->launches += 2;
         QCUDA(S, cudaStreamSynchronize(st_));
         n_wide = S->h_counts[0];
         const int n_found = S->h_counts[1];
         if (n_found > 0) rollout_list(listF, n_found);  // writes the accepted trajectory (same cost, accepted)
         s = 1 - s;
       }
-      k_compact<<<1, 1024, 0, st_>>>(active, n_active, st.phase, listS[0], listA[1 - cur], S->d_counts);
-      ++S->launches;
+      launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
       QCUDA(S, cudaStreamSynchronize(st_));
       n_next = S->h_counts[1];
     }
@@ -468,6 +502,8 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
       if (Q[12 * i + j] != 0.0 || Q[12 * j + i] != 0.0) S->q_block_diagonal = false;
   if (const char *e = std::getenv("QILQR_BACKWARD")) {  // debugging aid: "t1" forces the per-thread kernel
     if (std::string(e) == "t1") S->q_block_diagonal = false;
+    if (std::string(e) == "split") S->split_backward = true;
+    if (std::string(e) == "fused") S->split_backward = false;
   }
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);
@@ -497,7 +533,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
   cudaStreamSynchronize(S->stream);
   for (DeviceBuffer *b : {&S->buf1, &S->gk, &S->gK, &S->state_d, &S->state_i, &S->lists, &S->desired_soa,
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
-                          &S->debug_d, &S->misc, &S->wide_d})
+                          &S->debug_d, &S->misc, &S->wide_d, &S->rec_d})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);

@@ -714,6 +714,86 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
   }
 }
 
+// Multi-block version for long lists: pass 1 counts per 1024-entry chunk, pass 2 scans the chunk
+// counts (at most 2048 chunks) and scatters in order.
+__global__ void __launch_bounds__(1024) k_compact_count(const int *list_in, int n_in, const int *phase, int *chunk_counts,
+                                                       int phase_s, int phase_a) {
+  __shared__ int ws[32], wa[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int idx = blockIdx.x * 1024 + tid;
+  int ph = -1;
+  if (idx < n_in) ph = phase[list_in ? list_in[idx] : idx];
+  const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
+  const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
+  if (lane == 0) { ws[wid] = __popc(ms); wa[wid] = __popc(ma); }
+  __syncthreads();
+  if (wid == 0) {
+    int vs = ws[lane], va = wa[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { vs += __shfl_xor_sync(0xffffffffu, vs, o); va += __shfl_xor_sync(0xffffffffu, va, o); }
+    if (lane == 0) { chunk_counts[2 * blockIdx.x] = vs; chunk_counts[2 * blockIdx.x + 1] = va; }
+  }
+}
+__global__ void __launch_bounds__(1024) k_compact_scatter(const int *list_in, int n_in, const int *phase,
+                                                         const int *chunk_counts, int *out_search, int *out_active,
+                                                         volatile int *counts, int phase_s, int phase_a) {
+  __shared__ int ws[32], wa[32];
+  __shared__ int base_s, base_a;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // exclusive prefix of the chunk counts before this block (and the grand total for the last block)
+  int ps = 0, pa = 0, ts = 0, ta = 0;
+  for (int j = tid; j < int(gridDim.x); j += 1024) {
+    const int cs = chunk_counts[2 * j], ca = chunk_counts[2 * j + 1];
+    ts += cs; ta += ca;
+    if (j < int(blockIdx.x)) { ps += cs; pa += ca; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ps += __shfl_xor_sync(0xffffffffu, ps, o); pa += __shfl_xor_sync(0xffffffffu, pa, o);
+    ts += __shfl_xor_sync(0xffffffffu, ts, o); ta += __shfl_xor_sync(0xffffffffu, ta, o);
+  }
+  if (lane == 0) { ws[wid] = ps; wa[wid] = pa; }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0, b2 = 0;
+    for (int w = 0; w < 32; ++w) { a += ws[w]; b2 += wa[w]; }
+    base_s = a; base_a = b2;
+  }
+  __syncthreads();
+  // totals: every warp holds partial (ts, ta); reduce through shared memory in block 0 only
+  __shared__ int tsw[32], taw[32];
+  if (lane == 0) { tsw[wid] = ts; taw[wid] = ta; }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    int a = 0, b2 = 0;
+    for (int w = 0; w < 32; ++w) { a += tsw[w]; b2 += taw[w]; }
+    counts[0] = a; counts[1] = b2;
+    __threadfence_system();
+  }
+  const int idx = blockIdx.x * 1024 + tid;
+  int b = -1, ph = -1;
+  if (idx < n_in) { b = list_in ? list_in[idx] : idx; ph = phase[b]; }
+  const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
+  const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
+  __syncthreads();
+  if (lane == 0) { ws[wid] = __popc(ms); wa[wid] = __popc(ma); }
+  __syncthreads();
+  if (wid == 0) {
+    int vs = ws[lane], va = wa[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int xs = __shfl_up_sync(0xffffffffu, vs, o), xa = __shfl_up_sync(0xffffffffu, va, o);
+      if (lane >= o) { vs += xs; va += xa; }
+    }
+    ws[lane] = vs; wa[lane] = va;
+  }
+  __syncthreads();
+  const int off_s = base_s + (wid ? ws[wid - 1] : 0) + __popc(ms & ((1u << lane) - 1));
+  const int off_a = base_a + (wid ? wa[wid - 1] : 0) + __popc(ma & ((1u << lane) - 1));
+  if (ph == phase_s) out_search[off_s] = b;
+  if (ph == phase_a) out_active[off_a] = b;
+}
+
 // ---------------------------------------------------------------------------
 // Solve set-up / tear-down
 // ---------------------------------------------------------------------------
