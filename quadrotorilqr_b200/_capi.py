@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqilqr_b200.so")
+LIB_PATH = os.environ.get("QILQR_LIB") or os.path.join(_HERE, "libqilqr_b200.so")  # QILQR_LIB: tuning builds
 
 OK = 0
 ERR_INVALID_ARGUMENT = 1

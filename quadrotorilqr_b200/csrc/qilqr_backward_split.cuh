@@ -25,7 +25,7 @@ namespace g4 {
 constexpr int RECT = 100;             // record elements actually used (REC = 101 has one pad element)
 constexpr int TILE = RECT * 8;        // doubles per (tile, knot): 6400 B, a multiple of 16
 constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
-constexpr int SPLIT_SMEM_DOUBLES = 2 * TILE + 8 * XS + 36 * 8 + 2;
+constexpr int SPLIT_SMEM_DOUBLES = 2 * TILE + 8 * XS + 36 + 2;
 
 QD uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 QD void mbar_init(uint64_t *bar, int count) {
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
   double *bufs = smem;
   double *xch = smem + 2 * TILE + q * XS;
   double *s2Qvv = smem + 2 * TILE + 8 * XS;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36 * 8);
-  for (int e = lane; e < 36; e += 32) s2Qvv[e * 8] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36);
+  for (int e = lane; e < 36; e += 32) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);

@@ -64,6 +64,8 @@ QD void store_point(double *traj, int i, int B, int b, const double *x, const do
   for (int c = 0; c < 4; ++c) traj[row_index(i, 13 + c, 17, B, b)] = u[c];
 }
 
+QD void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 // ILQR::is_converged (ilqr.hh:196-205)
 QD bool is_converged(const DeviceParams &p, double cost, double new_cost) {
   const double d = fabs(cost - new_cost);
@@ -112,7 +114,10 @@ struct RolloutArgs {
   int palpha;        // MODE_WIDE: step sizes evaluated per problem
 };
 
-__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
+#ifndef QILQR_ROLLOUT_MINB
+#define QILQR_ROLLOUT_MINB 2
+#endif
+__global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int wide_j = (a.mode == MODE_WIDE) ? tid / a.n : 0;  // j-major so that a warp covers consecutive problems
   const int t = (a.mode == MODE_WIDE) ? tid % a.n : tid;

@@ -4,7 +4,7 @@
 // memory, stride RS = 1) and the split kernel (k_riccati_g4: record tiles [elem][8 problems]
 // brought in by TMA bulk copies, stride RS = 8).  See qilqr_backward_g4.cuh for the algorithm.
 //   rec    : this knot's linearisation record, element e at rec[e * RS]
-//   s2Qvv  : 2*Q_vv (6x6), element e at s2Qvv[e * RS]
+//   s2Qvv  : 2*Q_vv (6x6), dense
 //   xch    : this problem's exchange area (g4::XCH doubles)
 //   V0..V3 : the lane's column block c of V_xx (in/out);  vx: v_x (replicated, in/out)
 // =============================================================================
@@ -142,12 +142,13 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
   {
     // C_xx[r,:]: rows 0..5 come from the record's pose block, rows 6..11 from 2 Q_vv
     const bool lo = c < 2;
-    const double *src = lo ? (rec + (R_CPP + 18 * c) * RS) : (s2Qvv + 18 * (c - 2) * RS);
+    const double *src = lo ? (rec + (R_CPP + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
+    const int sst = lo ? RS : 1;  // the record is strided, the 2*Q_vv table is dense
 #pragma unroll
     for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
       for (int cj = 0; cj < 3; ++cj) {
-        const double a0 = src[(6 * ri + cj) * RS], a1 = src[(6 * ri + 3 + cj) * RS];
+        const double a0 = src[(6 * ri + cj) * sst], a1 = src[(6 * ri + 3 + cj) * sst];
         Q0[3 * ri + cj] = lo ? a0 : 0.0;
         Q1[3 * ri + cj] = lo ? a1 : 0.0;
         Q2[3 * ri + cj] = lo ? 0.0 : a0;
