@@ -68,7 +68,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -162,8 +162,8 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--seed", type=int, default=2026)
@@ -377,6 +377,16 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # algorithmic HBM bytes of the backward kernel: read 17 doubles (+17 desired if per-problem), write 52
     bwd_bytes = bwd_knots * (17 + 52) * 8.0
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        n_bwd_launches = max(1, ser["solver_iterations"])
+        traffic = tj["backward_dram_bytes_per_problem_knot"] * bwd_knots / n_bwd_launches
+        traffic_note = ("dram__bytes_read+write per problem-knot from the committed ncu capture (profiles/r1_traffic.json: "
+                        f"{tj['backward_dram_bytes_per_problem_knot']:.0f} B vs {tj['algorithmic_bytes_per_problem_knot']:.0f} B "
+                        "algorithmic; the difference is the linearisation record round trip) x mean problem-knots per launch")
+    except Exception:
+        pass
     roofline = {
         "kernel": "backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)",
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
@@ -385,7 +395,7 @@ def main():
                        "MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_problem_knot": F_BWD,
         "flops_definition": "dense as-written reference arithmetic counted by the oracle's FLOP-counting scalar",
-        "traffic": None,
+        "traffic": traffic, "traffic_note": traffic_note,
         "share_of_step": bwd_ms / (serial_ms * n_serial),
         "timed": f"CUDA events around every launch of {n_serial} un-pipelined steps run right after the timed region",
         "hbm": {"achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "peak": hbm_peak,
