@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(32) k_backward_g4(const __grid_constant__ Devi
   double *s2Qvv = smem + 8 * S;
   for (int e = lane; e < 36; e += 32) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
 
-  double V0[9], V1[9], V2[9], V3[9], vx[12];
+  double V0[9], V1[9], V2[9], V3[9], vx[12], V88[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) V88[e] = 0.0;
 #pragma unroll
   for (int e = 0; e < 9; ++e) V0[e] = V1[e] = V2[e] = V3[e] = 0.0;
 #pragma unroll
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(32) k_backward_g4(const __grid_constant__ Devi
     for (int j = 0; j < KPP; ++j) {
       const int ii = i - j;
       if (ii < 0) break;
-      riccati_step<1>(p, a, recs + j * REC, s2Qvv, xch, c, valid, ii, B, b, V0, V1, V2, V3, vx, QuTk, kTQuuk);
+      riccati_step<1>(p, a, recs + j * REC, s2Qvv, xch, c, valid, ii, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
     }
   }
 

@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
   }
   uint32_t phase0 = 0, phase1 = 0;
 
-  double V0[9], V1[9], V2[9], V3[9], vx[12];
+  double V0[9], V1[9], V2[9], V3[9], vx[12], V88[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) V88[e] = 0.0;
 #pragma unroll
   for (int e = 0; e < 9; ++e) V0[e] = V1[e] = V2[e] = V3[e] = 0.0;
 #pragma unroll
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
     }
     if (s == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
     else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-    riccati_step<8>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, QuTk, kTQuuk);
+    riccati_step<8>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
   }
 
   if (!valid || c != 0) return;

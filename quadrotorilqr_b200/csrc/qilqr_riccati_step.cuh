@@ -7,6 +7,7 @@
 //   s2Qvv  : 2*Q_vv (6x6), dense
 //   xch    : this problem's exchange area (g4::XCH doubles)
 //   V0..V3 : the lane's column block c of V_xx (in/out);  vx: v_x (replicated, in/out)
+//   V88    : V_xx[8:12, 8:12] (replicated, in/out) -- all that Q_uu = C_uu + B^T V_xx B needs
 // =============================================================================
 #pragma once
 // (included by qilqr_backward_g4.cuh after the g4 helpers it uses)
@@ -22,7 +23,7 @@ QD void ld9s(const double *s, double *r) {
 template <int RS>
 QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double *rec, const double *s2Qvv,
                      double *xch, const int c, const bool valid, const int ii, const int B, const int b, double *V0,
-                     double *V1, double *V2, double *V3, double *vx, double &QuTk, double &kTQuuk) {
+                     double *V1, double *V2, double *V3, double *vx, double *V88, double &QuTk, double &kTQuuk) {
   const double dgz[3] = {rec[R_GZ * RS], rec[(R_GZ + 1) * RS], rec[(R_GZ + 2) * RS]};
   const double ndgz[3] = {-dgz[0], -dgz[1], -dgz[2]};
 
@@ -49,31 +50,15 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     ld9s<RS>(rec + R_WD * RS, Tb);
     m3_maddT(Tb, V3, Mb);
     st9(xch + moff(3, c), Mb);
-    // V[8:12, 8:12] for Q_uu: lane 2 owns column 8, lane 3 columns 9..11
-    if (c == 2) {
-      xch[X_Q + 0] = V2[8];
-      xch[X_Q + 4] = V3[2];
-      xch[X_Q + 8] = V3[5];
-      xch[X_Q + 12] = V3[8];
-    } else if (c == 3) {
-#pragma unroll
-      for (int jj = 0; jj < 3; ++jj) {
-        xch[X_Q + 1 + jj] = V2[6 + jj];
-        xch[X_Q + 5 + jj] = V3[jj];
-        xch[X_Q + 9 + jj] = V3[3 + jj];
-        xch[X_Q + 13 + jj] = V3[6 + jj];
-      }
-    }
   }
-  __syncwarp();
 
   // ---------------- step 2 (replicated): Q_uu, Q_u, Q_x, factorisation, k ----------------
+  // (independent of step 1: no barrier in between, so the factorisation's dependency chain overlaps the
+  //  block products above)
   double Quu[16], Qu[4], Qx[12], k[4];
   Ldlt4 f;
   {
-    double V88[16], BtV[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) V88[e] = xch[X_Q + e];
+    double BtV[16];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
@@ -136,6 +121,8 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) k[jj] = -rhs[jj];
   }
+
+  __syncwarp();
 
   // ---------------- step 3: row block r = c of Q_xx and Q_xu ----------------
   double Q0[9], Q1[9], Q2[9], Q3[9], Qxu[12];
@@ -226,11 +213,12 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         xch[X_K + 12 * jj + 3 * c + s] = Ks[3 * jj + s];
-        if (valid) a.pr.gK[row_index(ii, 12 * jj + 3 * c + s, 48, B, b)] = Ks[3 * jj + s];
+        a.pr.gK[row_index(ii, 12 * jj + 3 * c + s, 48, B, b)] = Ks[3 * jj + s];  // tail quads rewrite identical values
       }
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (valid && c == jj) a.pr.gk[row_index(ii, jj, 4, B, b)] = k[jj];
+    {
+      const double kc = (c == 0) ? k[0] : (c == 1) ? k[1] : (c == 2) ? k[2] : k[3];
+      a.pr.gk[row_index(ii, c, 4, B, b)] = kc;
+    }
   }
   __syncwarp();
 
@@ -285,6 +273,15 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
   ld9(xch + moff(1, c), V1);
   ld9(xch + moff(2, c), V2);
   ld9(xch + moff(3, c), V3);
+  V88[0] = xch[moff(2, 2) + 8];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    V88[1 + e] = xch[moff(2, 3) + 6 + e];
+    V88[4 * (1 + e)] = xch[moff(3, 2) + 3 * e + 2];
+    V88[5 + e] = xch[moff(3, 3) + e];
+    V88[9 + e] = xch[moff(3, 3) + 3 + e];
+    V88[13 + e] = xch[moff(3, 3) + 6 + e];
+  }
   if (p.symmetrize_vxx) {  // V <- (V + V^T)/2: block (K,c) needs (block (c,K))^T, which this lane owns
 #pragma unroll
     for (int ri = 0; ri < 3; ++ri)
@@ -294,6 +291,14 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
         V1[3 * ri + cj] = 0.5 * (V1[3 * ri + cj] + Q1[3 * cj + ri]);
         V2[3 * ri + cj] = 0.5 * (V2[3 * ri + cj] + Q2[3 * cj + ri]);
         V3[3 * ri + cj] = 0.5 * (V3[3 * ri + cj] + Q3[3 * cj + ri]);
+      }
+#pragma unroll
+    for (int r8 = 0; r8 < 4; ++r8)
+#pragma unroll
+      for (int c8 = r8 + 1; c8 < 4; ++c8) {
+        const double m8 = 0.5 * (V88[4 * r8 + c8] + V88[4 * c8 + r8]);
+        V88[4 * r8 + c8] = m8;
+        V88[4 * c8 + r8] = m8;
       }
   }
   __syncwarp();
