@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Small solves exercising every kernel, for compute-sanitizer (memcheck / racecheck / initcheck):
+   compute-sanitizer --tool racecheck python tools/sanitizer_case.py"""
+import dataclasses
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quadrotorilqr_b200 import BatchILQR, problems  # noqa: E402
+
+
+def run(opts, B, N, env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = v
+    m = problems.hover_model()
+    s = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"], m["Q"],
+                  m["R"], m["dt_s"], opts)
+    for k in (env or {}):
+        del os.environ[k]
+    d = problems.hover_desired_trajectory(N)
+    x0 = problems.hover_initial_states(B, seed=3)
+    seed = problems.constant_state_trajectory(x0, N, m["dt_s"], d[0, 14:18])
+    init = s.forward_sim(seed, np.zeros((B, N, 4)), np.zeros((B, N, 48)))
+    r = s.solve(init, d, want_gains=True, hist_cap=20, want_debug=opts.populate_debug)
+    return r["results"]
+
+
+if __name__ == "__main__":
+    base = dataclasses.replace(problems.default_options(False))
+    base.convergence_criteria.max_iters = 6.0
+    print(run(base, 21, 9)["backward_passes"])                                        # split backward (default)
+    print(run(base, 13, 6, {"QILQR_BACKWARD": "fused"})["backward_passes"])           # fused quad kernel
+    print(run(dataclasses.replace(base, num_parallel_alphas=3, symmetrize_vxx=True, populate_debug=True), 10, 7)["rollouts"])
+    print(run(base, 5, 5, {"QILQR_BACKWARD": "t1"})["backward_passes"])               # thread-per-problem kernel
