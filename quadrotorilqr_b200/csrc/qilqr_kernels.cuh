@@ -676,7 +676,7 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, const int *phase, int *out_search,
                                                  int *out_active, volatile int *counts, int phase_s = PHASE_SEARCH,
-                                                 int phase_a = PHASE_ACTIVE) {
+                                                 int phase_a = PHASE_ACTIVE, int seq = 0) {
   __shared__ int warp_s[32], warp_a[32];
   __shared__ int base_s, base_a;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -716,6 +716,7 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
     counts[0] = base_s;
     counts[1] = base_a;
     __threadfence_system();
+    if (seq) { counts[2] = seq; __threadfence_system(); }  // the host polls this word (mapped pinned memory)
   }
 }
 
@@ -741,7 +742,7 @@ __global__ void __launch_bounds__(1024) k_compact_count(const int *list_in, int 
 }
 __global__ void __launch_bounds__(1024) k_compact_scatter(const int *list_in, int n_in, const int *phase,
                                                          const int *chunk_counts, int *out_search, int *out_active,
-                                                         volatile int *counts, int phase_s, int phase_a) {
+                                                         volatile int *counts, int phase_s, int phase_a, int seq) {
   __shared__ int ws[32], wa[32];
   __shared__ int base_s, base_a;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -774,6 +775,7 @@ __global__ void __launch_bounds__(1024) k_compact_scatter(const int *list_in, in
     for (int w = 0; w < 32; ++w) { a += tsw[w]; b2 += taw[w]; }
     counts[0] = a; counts[1] = b2;
     __threadfence_system();
+    if (seq) { counts[2] = seq; __threadfence_system(); }
   }
   const int idx = blockIdx.x * 1024 + tid;
   int b = -1, ph = -1;
