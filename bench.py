@@ -324,7 +324,7 @@ def main():
         def host_step(j, acc=None):
             solvers[j].solve_host_buffers(init_host, desired_c, out_host[j], res_host[j])
 
-        e2e_steps = max(P, min(args.steps, 4))
+        e2e_steps = max(P, args.steps)
         run_pipelined(host_step, P)
         barrier()
         t0 = time.perf_counter()
