@@ -1,0 +1,90 @@
+"""BASELINE.json's full size (batch 65536, N = 40) checked through size-independent properties, plus an
+oracle spot check on a random sample: the headline workload is correct, not just fast."""
+import numpy as np
+import pytest
+
+from conftest import make_solver, oracle_config
+
+pytestmark = pytest.mark.gpu
+
+B, N = 65536, 40
+
+
+@pytest.fixture(scope="module")
+def full_batch():
+    from quadrotorilqr_b200 import problems
+
+    model, opts = problems.hover_model(), problems.default_options(False)
+    s = make_solver(model, opts)
+    desired = problems.hover_desired_trajectory(N, model["dt_s"], model["mass_kg"], model["g_mpss"])
+    x0 = problems.hover_initial_states(B, seed=2026)
+    seedtraj = problems.constant_state_trajectory(x0, N, model["dt_s"], desired[0, 14:18])
+    initial = s.forward_sim(seedtraj, np.zeros((B, N, 4)), np.zeros((B, N, 48)))
+    r = s.solve(initial, desired, hist_cap=100)
+    return s, model, opts, desired, initial, r
+
+
+def test_statuses_counts_and_cost_histories(full_batch):
+    s, model, opts, desired, initial, r = full_batch
+    res, hist = r["results"], r["cost_history"]
+    assert np.all(np.isin(res["status"], [1, 2, 3]))                     # no line-search failures on this workload
+    assert np.mean(np.isin(res["status"], [1, 2])) > 0.999               # converged fraction
+    assert res["backward_passes"].min() >= 2 and res["backward_passes"].max() <= 100
+    # solve() bookkeeping invariants (ilqr.hh:53-87): exit A -> one more backward pass than completed
+    # iterations; exits B and C -> equal; rollouts >= completed iterations
+    nd, bp = res["num_debug"], res["backward_passes"]
+    assert np.all(bp[res["status"] == 1] == nd[res["status"] == 1] + 1)
+    assert np.all(bp[res["status"] != 1] == nd[res["status"] != 1])
+    assert np.all(res["rollouts"] >= nd)
+    # Armijo: after the unconditional first step every accepted step decreases the cost
+    idx = np.arange(100)[None, :]
+    valid = (idx >= 1) & (idx < nd[:, None])
+    dec = hist[:, 1:] - hist[:, :-1]
+    assert np.all(dec[valid[:, 1:]] < 0.0)
+    # final_cost is the last history entry, and it is the cost of the returned trajectory
+    last = hist[np.arange(B), np.maximum(nd - 1, 0)]
+    assert np.array_equal(last, res["final_cost"])
+    sample = np.random.default_rng(0).choice(B, 512, replace=False)
+    c = s.cost_trajectory(r["traj"][sample], desired)
+    assert np.array_equal(c, res["final_cost"][sample])
+
+
+def test_returned_trajectories_satisfy_the_dynamics(full_batch):
+    s, model, opts, desired, initial, r = full_batch
+    traj = r["traj"]
+    assert np.array_equal(traj[:, 0, 1:14], initial[:, 0, 1:14])        # x0 is kept (ilqr.hh:156)
+    assert np.array_equal(traj[:, :, 0], initial[:, :, 0])              # time_s copied through (ilqr.hh:164)
+    sample = np.random.default_rng(1).choice(B, 256, replace=False)
+    x = traj[sample][:, :-1, 1:14].reshape(-1, 13)
+    u = traj[sample][:, :-1, 14:18].reshape(-1, 4)
+    xn = s.discrete_dynamics(x, u).reshape(len(sample), N - 1, 13)
+    assert np.array_equal(xn, traj[sample][:, 1:, 1:14])                # bit-exact: same device function
+    q = traj[:, :, 4:8]
+    assert np.max(np.abs(np.sum(q * q, axis=2) - 1.0)) < 1e-12          # quaternions stay normalised
+
+
+def test_batch_composition_invariance_at_full_size(full_batch):
+    s, model, opts, desired, initial, r = full_batch
+    sample = np.sort(np.random.default_rng(2).choice(B, 300, replace=False))
+    sub = s.solve(initial[sample], desired, hist_cap=100)
+    assert np.array_equal(sub["traj"], r["traj"][sample])
+    assert np.array_equal(sub["results"], r["results"][sample])
+    assert np.array_equal(sub["cost_history"], r["cost_history"][sample])
+
+
+def test_oracle_spot_check_at_full_size(O, full_batch):
+    s, model, opts, desired, initial, r = full_batch
+    cfg = oracle_config(O, model, opts)
+    res = r["results"]
+    # the slowest problems (including the ones that hit max_iters) and a random sample
+    hard = np.argsort(-res["backward_passes"])[:8]
+    sample = np.unique(np.concatenate([hard, np.random.default_rng(3).choice(B, 40, replace=False)]))
+    o = O.solve_batch(cfg, desired, initial[sample], hist_cap=100)
+    assert np.array_equal(res["status"][sample], o["status"])
+    assert np.array_equal(res["backward_passes"][sample], o["backward_passes"])
+    assert np.array_equal(res["rollouts"][sample], o["rollouts"])
+    for j, b in enumerate(sample):
+        err = np.max(np.abs(r["traj"][b] - o["traj"][j]))
+        assert err <= 1e-9 * max(1.0, np.max(np.abs(o["traj"][j]))), (b, err)
+        herr = np.max(np.abs(r["cost_history"][b] - o["cost_history"][j]))
+        assert herr <= 1e-9 * max(1.0, np.max(np.abs(o["cost_history"][j]))), (b, herr)
