@@ -260,7 +260,8 @@ int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   const int n8 = (ba.n + 7) & ~7;
   const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * g4::TILE / 8;
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
-  const size_t smem = sizeof(double) * g4::SPLIT_SMEM_DOUBLES;
+  static const size_t extra = std::getenv("QILQR_RICCATI_EXTRA_SMEM") ? std::atoi(std::getenv("QILQR_RICCATI_EXTRA_SMEM")) : 0;
+  const size_t smem = sizeof(double) * g4::SPLIT_SMEM_DOUBLES + extra;  // `extra`: occupancy experiments only
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_riccati_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
