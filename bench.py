@@ -59,23 +59,32 @@ class ClockSampler:
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
 
     def _run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        # one streaming nvidia-smi (-lms) instead of a process per sample: ~10 samples per second
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 6:
                     self.samples.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.05)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
 
     def start(self):
+        self.proc = None
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+        time.sleep(0.25)  # let the first sample arrive before the timed region starts
 
     def stop(self):
         self.stop_flag = True
+        if getattr(self, "proc", None) is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         if self.thread:
             self.thread.join(timeout=6)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
