@@ -179,7 +179,6 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-serial", action="store_true")
     ap.add_argument("--pipeline", type=int, default=8,
                     help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
     args = ap.parse_args()
