@@ -274,9 +274,10 @@ int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   ++S->launches;
   return QILQR_OK;
 }
-void launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
+int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
   if (S->q_block_diagonal && S->split_backward) {
-    launch_split(S, ba);
+    const int rc = launch_split(S, ba);
+    if (rc) return fail(S, rc, "out of device memory for the linearisation records");
   } else if (!S->q_block_diagonal) {
     k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->cur>>>(S->p, ba);
   } else if (S->g4_kpp == 1) {
@@ -286,6 +287,7 @@ void launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
   } else {
     launch_g4<4>(S, ba);
   }
+  return QILQR_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -342,7 +344,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     BackwardArgs ba{pr, st, active, n_active, i, wide ? PHASE_WIDE : PHASE_SEARCH, 1, nullptr, nullptr};
     {
       SpanGuard g(S, 0);
-      launch_backward(S, ba);
+      if ((rc = launch_backward(S, ba))) return rc;
     }
     S->stats.backward_problem_knots += int64_t(n_active) * N;
     S->stats.problem_iterations += n_active;
@@ -825,7 +827,7 @@ int qilqr_backwards_pass_host(qilqr_solver_t *S, int B, int N, const double *des
   if (rc) return rc;
   Problem pr{B, N, Bd, nullptr, nullptr, S->desired_soa.as<double>(), S->gk.as<double>(), S->gK.as<double>()};
   BackwardArgs ba{pr, SolveState{}, nullptr, B, 0, PHASE_SEARCH, 0, S->traj_soa.as<double>(), S->misc.as<double>()};
-  launch_backward(S, ba);
+  if ((rc = launch_backward(S, ba))) return rc;
   ++S->launches;
   transpose_to_aos(S, S->gk.as<double>(), S->stage_c.as<double>(), B, N, 4);
   QCUDA(S, cudaMemcpyAsync(k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
