@@ -66,6 +66,14 @@ QD void store_point(double *traj, int i, int B, int b, const double *x, const do
 
 QD void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// A global load the compiler may not sink towards its first use (volatile asm keeps program order):
+// lets a kernel issue all the loads of a loop iteration up front, ahead of long dependent arithmetic.
+QD double ldg_early(const double *ptr) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  return v;
+}
+
 // ILQR::is_converged (ilqr.hh:196-205)
 QD bool is_converged(const DeviceParams &p, double cost, double new_cost) {
   const double d = fabs(cost - new_cost);
@@ -147,18 +155,26 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
   load_point(cur, 0, B, b, x, ubar);  // state = current_traj.front().state (ilqr.hh:156)
   double cost = 0.0;
   for (int i = 0; i < N; ++i) {
-    double xbar[13];
-    load_point(cur, i, B, b, xbar, ubar);
+    // every load of this knot is issued here, before the long dependent chain of state_minus: the
+    // gains arrive in its shadow instead of stalling the feedback product
+    double xbar[13], gk[4], gK[48];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) xbar[c] = ldg_early(&cur[row_index(i, c, 17, B, b)]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ubar[c] = ldg_early(&cur[row_index(i, 13 + c, 17, B, b)]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gk[e] = ldg_early(&a.pr.gk[row_index(i, e, 4, B, b)]);
+#pragma unroll
+    for (int e = 0; e < 48; ++e) gK[e] = ldg_early(&a.pr.gK[row_index(i, e, 48, B, b)]);
     double d[12];
     state_minus(x, xbar, d, nullptr);  // (state - current_traj[i].state).coeffs()
     double u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const double kj = a.pr.gk[row_index(i, j, 4, B, b)];
-      double Kd = a.pr.gK[row_index(i, 12 * j, 48, B, b)] * d[0];
+      double Kd = gK[12 * j] * d[0];
 #pragma unroll
-      for (int s = 1; s < 12; ++s) Kd = fma(a.pr.gK[row_index(i, 12 * j + s, 48, B, b)], d[s], Kd);
-      u[j] = (ubar[j] + alpha * kj) + Kd;
+      for (int s = 1; s < 12; ++s) Kd = fma(gK[12 * j + s], d[s], Kd);
+      u[j] = (ubar[j] + alpha * gk[j]) + Kd;
     }
     if (a.mode != MODE_WIDE) store_point(cand, i, B, b, x, u);
     if (want_cost) {
