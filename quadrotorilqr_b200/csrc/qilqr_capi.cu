@@ -708,6 +708,7 @@ int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int
   if (want_debug) {
     QCUDA(S, S->debug_d.ensure(sizeof(double) * size_t(debug_cap) * N * 17 * B));
     d_debug = S->debug_d.as<double>();
+    QCUDA(S, cudaMemsetAsync(d_debug, 0, sizeof(double) * size_t(debug_cap) * N * 17 * B, st_));  // slots a problem never reaches
   }
   QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
   rc = solve_core(S, B, N, S->desired_soa.as<double>(), Bd, S->traj_soa.as<double>(), d_k, d_K, d_hist, hist_cap,
