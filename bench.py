@@ -207,6 +207,8 @@ def main():
     torch.cuda.set_device(dev)
 
     m, opts = problems.hover_model(), problems.default_options(False)
+    if os.environ.get("QILQR_BENCH_MAX_ITERS"):  # diagnosis only (cuts the max_iters tail); not the BASELINE config
+        opts.convergence_criteria.max_iters = float(os.environ["QILQR_BENCH_MAX_ITERS"])
     B, N = args.batch, N_KNOTS
     P = max(1, args.pipeline)
 
