@@ -32,6 +32,7 @@ namespace qilqr {
 
 namespace g4 {
 constexpr int R_RE = 0, R_TE = 9, R_DJR = 18, R_DQB = 27, R_GZ = 36, R_WD = 39, R_CX = 48, R_CU = 60, R_CPP = 64;
+constexpr int R_CPV = 100, R_CVP = 136;  // only in records of a Q with pose/velocity coupling (172 doubles)
 constexpr int REC = 101;  // = 5 (mod 16)
 constexpr int X_M = 0, X_K = 148, X_VX = 196, X_Q = 208, XCH = 224;
 __host__ __device__ constexpr int stride(int kpp) {
@@ -73,8 +74,9 @@ QD void m3_madd_hat(const double *M, const double *w, double *C) {
   }
 }
 
-// Linearise one knot into a record whose element e lives at rec[e * RS] (requires Q_pv = Q_vp = 0).
-template <int RS = 1>
+// Linearise one knot into a record whose element e lives at rec[e * RS].  DENSEQ = false requires
+// Q_pv = Q_vp = 0 (100-double record); DENSEQ = true handles any Q (172-double record).
+template <int RS = 1, bool DENSEQ = false>
 QD void linearise_to_record(const DeviceParams &p, const double *x, const double *u, const double *xd,
                             const double *ud, double *rec) {
   {
@@ -93,18 +95,28 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
   Angle ang;
   state_minus(x, xd, dx, Jli, &ang);
   se3_rjacinv_blocks(dx, Jli, ang, Ji, Qi);
-  // y = (2 dx)^T Q with Q = blkdiag(Qpp, Qvv)
+  // y = (2 dx)^T Q   (with Q = blkdiag(Qpp, Qvv) when !DENSEQ: the skipped terms are exact zeros)
   double y[12];
+  if (DENSEQ) {
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double s = (2.0 * dx[0]) * p.Q[j];
+    for (int j = 0; j < 12; ++j) {
+      double s = (2.0 * dx[0]) * p.Q[j];
 #pragma unroll
-    for (int i = 1; i < 6; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
-    y[j] = s;
-    double s2 = (2.0 * dx[6]) * p.Q[72 + 6 + j];
+      for (int i = 1; i < 12; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+      y[j] = s;
+    }
+  } else {
 #pragma unroll
-    for (int i = 7; i < 12; ++i) s2 = fma(2.0 * dx[i], p.Q[12 * i + 6 + j], s2);
-    y[6 + j] = s2;
+    for (int j = 0; j < 6; ++j) {
+      double s = (2.0 * dx[0]) * p.Q[j];
+#pragma unroll
+      for (int i = 1; i < 6; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+      y[j] = s;
+      double s2 = (2.0 * dx[6]) * p.Q[72 + 6 + j];
+#pragma unroll
+      for (int i = 7; i < 12; ++i) s2 = fma(2.0 * dx[i], p.Q[12 * i + 6 + j], s2);
+      y[6 + j] = s2;
+    }
   }
   double Cx[6];
   m3T_vec(Ji, y, Cx);
@@ -119,12 +131,14 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
     for (int l = 1; l < 4; ++l) s = fma(2.0 * (u[l] - ud[l]), p.R[4 * l + j], s);
     rec[(R_CU + j) * RS] = s;
   }
-  // Cpp = ((2 J6^T) Qpp) J6, J6 = [[Ji, Qi], [0, Ji]]
+  // C_xx = ((2 J^T) Q) J with J = blkdiag(J6, I), J6 = [[Ji, Qi], [0, Ji]]:
+  //   rows 0..5 of P = (2 J^T) Q are (2 J6^T) Q[0:6, :];  C_pp = P[:, 0:6] J6,  C_pv = P[:, 6:12]
+  constexpr int PC = DENSEQ ? 12 : 6;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    double Pa[6], Pb[6];  // rows i and 3+i of (2 J6^T) Qpp
+    double Pa[PC], Pb[PC];  // rows i and 3+i of P
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    for (int j = 0; j < PC; ++j) {
       Pa[j] = fma(2.0 * Ji[6 + i], p.Q[24 + j], fma(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
       double s = fma(2.0 * Qi[6 + i], p.Q[24 + j], fma(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
       s = fma(2.0 * Ji[i], p.Q[36 + j], s);
@@ -146,6 +160,31 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
       s2 = fma(Pb[4], Ji[3 + j], s2);
       s2 = fma(Pb[5], Ji[6 + j], s2);
       rec[(R_CPP + 6 * (3 + i) + 3 + j) * RS] = s2;
+    }
+    if (DENSEQ) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        rec[(R_CPV + 6 * i + j) * RS] = Pa[6 + (DENSEQ ? j : 0)];
+        rec[(R_CPV + 6 * (3 + i) + j) * RS] = Pb[6 + (DENSEQ ? j : 0)];
+      }
+    }
+  }
+  if (DENSEQ) {
+    // C_vp = P[6:12, 0:6] J6 with P[6+i, :] = 2 Q[6+i, :]
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double Pr[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Pr[k] = 2.0 * p.Q[12 * (6 + i) + k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        rec[(R_CVP + 6 * i + j) * RS] = fma(Pr[2], Ji[6 + j], fma(Pr[1], Ji[3 + j], Pr[0] * Ji[j]));
+        double s = fma(Pr[2], Qi[6 + j], fma(Pr[1], Qi[3 + j], Pr[0] * Qi[j]));
+        s = fma(Pr[3], Ji[j], s);
+        s = fma(Pr[4], Ji[3 + j], s);
+        s = fma(Pr[5], Ji[6 + j], s);
+        rec[(R_CVP + 6 * i + 3 + j) * RS] = s;
+      }
     }
   }
 }

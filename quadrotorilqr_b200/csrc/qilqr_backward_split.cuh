@@ -22,10 +22,12 @@
 namespace qilqr {
 namespace g4 {
 
-constexpr int RECT = 100;             // record elements actually used (REC = 101 has one pad element)
-constexpr int TILE = RECT * 8;        // doubles per (tile, knot): 6400 B, a multiple of 16
+// record elements per knot: 100 for Q = blkdiag(Q_pp, Q_vv), 172 for a Q with pose/velocity coupling
+__host__ __device__ constexpr int rect(bool denseq) { return denseq ? 172 : 100; }
+// doubles per (tile of 8 problems, knot): 6400 B / 11008 B, multiples of 16
+__host__ __device__ constexpr int tile_doubles(bool denseq) { return rect(denseq) * 8; }
 constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
-constexpr int SPLIT_SMEM_DOUBLES = 2 * TILE + 8 * XS + 36 + 2;
+__host__ __device__ constexpr int split_smem_doubles(bool denseq) { return 2 * tile_doubles(denseq) + 8 * XS + 36 + 2; }
 
 QD uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 QD void mbar_init(uint64_t *bar, int count) {
@@ -57,9 +59,11 @@ QD void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 // One thread per (slot, knot); slots are padded to whole tiles of 8 (padding replicates the last
 // problem so that every record is finite).  Consecutive threads = consecutive slots.
+template <bool DENSEQ>
 __global__ void __launch_bounds__(128) k_linearise(const __grid_constant__ DeviceParams p,
                                                    const __grid_constant__ BackwardArgs a, double *rec_g) {
   using namespace g4;
+  constexpr int TILE = tile_doubles(DENSEQ);
   const int n8 = (a.n + 7) & ~7;
   const size_t id = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int N = a.pr.N;
@@ -74,12 +78,14 @@ __global__ void __launch_bounds__(128) k_linearise(const __grid_constant__ Devic
   load_point(traj, i, B, b, x, u);
   load_point(a.pr.desired, i, Bd, bd, xd, ud);
   double *dst = rec_g + (size_t(t >> 3) * N + i) * TILE + (t & 7);
-  linearise_to_record<8>(p, x, u, xd, ud, dst);
+  linearise_to_record<8, DENSEQ>(p, x, u, xd, ud, dst);
 }
 
+template <bool DENSEQ>
 __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ DeviceParams p,
                                                    const __grid_constant__ BackwardArgs a, const double *rec_g) {
   using namespace g4;
+  constexpr int TILE = tile_doubles(DENSEQ);
   extern __shared__ __align__(128) double smem[];
   const int lane = threadIdx.x, c = lane & 3, q = lane >> 2;
   const int tile = blockIdx.x;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
     }
     if (s == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
     else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-    riccati_step<8>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
+    riccati_step<8, DENSEQ>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
   }
 
   if (!valid || c != 0) return;

@@ -68,6 +68,7 @@ struct qilqr_solver {
   bool profiling = false;
   bool q_block_diagonal = true;  // Q = blkdiag(Q_pp, Q_vv): the 4-lanes-per-problem backward kernel applies
   int g4_kpp = 4;                // knots linearised per phase by the quad kernel (1, 2 or 4)
+  bool force_t1 = false;         // QILQR_BACKWARD=t1: the one-thread-per-problem kernel (cross-checks)
   bool split_backward = true;    // linearise kernel + TMA-fed Riccati kernel (default) vs the fused quad kernel
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
@@ -256,29 +257,30 @@ void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
 }
 // ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
 // coupling, one-thread-per-problem kernel otherwise.
+template <bool DENSEQ>
 int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   const int n8 = (ba.n + 7) & ~7;
-  const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * g4::TILE / 8;
+  const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * g4::rect(DENSEQ);
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
   static const size_t extra = std::getenv("QILQR_RICCATI_EXTRA_SMEM") ? std::atoi(std::getenv("QILQR_RICCATI_EXTRA_SMEM")) : 0;
-  const size_t smem = sizeof(double) * g4::SPLIT_SMEM_DOUBLES + extra;  // `extra`: occupancy experiments only
+  const size_t smem = sizeof(double) * g4::split_smem_doubles(DENSEQ) + extra;  // `extra`: occupancy experiments only
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_riccati_g4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    cudaFuncSetAttribute(k_riccati_g4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   const size_t threads = size_t(n8) * ba.pr.N;
-  k_linearise<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
-  k_riccati_g4<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  k_linearise<DENSEQ><<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  k_riccati_g4<DENSEQ><<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   ++S->launches;
   return QILQR_OK;
 }
 int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
-  if (S->q_block_diagonal && S->split_backward) {
-    const int rc = launch_split(S, ba);
+  if (S->split_backward && !S->force_t1) {
+    const int rc = S->q_block_diagonal ? launch_split<false>(S, ba) : launch_split<true>(S, ba);
     if (rc) return fail(S, rc, "out of device memory for the linearisation records");
-  } else if (!S->q_block_diagonal) {
+  } else if (!S->q_block_diagonal || S->force_t1) {
     k_backward_t1<<<blocks_for(ba.n, 64), 64, 0, S->cur>>>(S->p, ba);
   } else if (S->g4_kpp == 1) {
     launch_g4<1>(S, ba);
@@ -527,7 +529,7 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
     for (int j = 6; j < 12; ++j)
       if (Q[12 * i + j] != 0.0 || Q[12 * j + i] != 0.0) S->q_block_diagonal = false;
   if (const char *e = std::getenv("QILQR_BACKWARD")) {  // debugging aid: "t1" forces the per-thread kernel
-    if (std::string(e) == "t1") S->q_block_diagonal = false;
+    if (std::string(e) == "t1") S->force_t1 = true;
     if (std::string(e) == "split") S->split_backward = true;
     if (std::string(e) == "fused") S->split_backward = false;
   }

@@ -20,7 +20,7 @@ QD void ld9s(const double *s, double *r) {
   for (int e = 0; e < 9; ++e) r[e] = s[e * RS];
 }
 
-template <int RS>
+template <int RS, bool DENSEQ = false>
 QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double *rec, const double *s2Qvv,
                      double *xch, const int c, const bool valid, const int ii, const int B, const int b, double *V0,
                      double *V1, double *V2, double *V3, double *vx, double *V88, double &QuTk, double &kTQuuk) {
@@ -127,20 +127,36 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
   // ---------------- step 3: row block r = c of Q_xx and Q_xu ----------------
   double Q0[9], Q1[9], Q2[9], Q3[9], Qxu[12];
   {
-    // C_xx[r,:]: rows 0..5 come from the record's pose block, rows 6..11 from 2 Q_vv
+    // C_xx[r,:] (cost.hh:52): rows 0..5 = [C_pp | C_pv] from the record, rows 6..11 = [C_vp | 2 Q_vv];
+    // C_pv and C_vp vanish (and are not stored) when Q has no pose/velocity coupling (!DENSEQ).
     const bool lo = c < 2;
-    const double *src = lo ? (rec + (R_CPP + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
-    const int sst = lo ? RS : 1;  // the record is strided, the 2*Q_vv table is dense
+    if (DENSEQ) {
+      const double *srcA = lo ? (rec + (R_CPP + 18 * c) * RS) : (rec + (R_CVP + 18 * (c - 2)) * RS);
+      const double *srcB = lo ? (rec + (R_CPV + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
+      const int sB = lo ? RS : 1;  // the record is strided, the 2*Q_vv table is dense
 #pragma unroll
-    for (int ri = 0; ri < 3; ++ri)
+      for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
-      for (int cj = 0; cj < 3; ++cj) {
-        const double a0 = src[(6 * ri + cj) * sst], a1 = src[(6 * ri + 3 + cj) * sst];
-        Q0[3 * ri + cj] = lo ? a0 : 0.0;
-        Q1[3 * ri + cj] = lo ? a1 : 0.0;
-        Q2[3 * ri + cj] = lo ? 0.0 : a0;
-        Q3[3 * ri + cj] = lo ? 0.0 : a1;
-      }
+        for (int cj = 0; cj < 3; ++cj) {
+          Q0[3 * ri + cj] = srcA[(6 * ri + cj) * RS];
+          Q1[3 * ri + cj] = srcA[(6 * ri + 3 + cj) * RS];
+          Q2[3 * ri + cj] = srcB[(6 * ri + cj) * sB];
+          Q3[3 * ri + cj] = srcB[(6 * ri + 3 + cj) * sB];
+        }
+    } else {
+      const double *src = lo ? (rec + (R_CPP + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
+      const int sst = lo ? RS : 1;
+#pragma unroll
+      for (int ri = 0; ri < 3; ++ri)
+#pragma unroll
+        for (int cj = 0; cj < 3; ++cj) {
+          const double a0 = src[(6 * ri + cj) * sst], a1 = src[(6 * ri + 3 + cj) * sst];
+          Q0[3 * ri + cj] = lo ? a0 : 0.0;
+          Q1[3 * ri + cj] = lo ? a1 : 0.0;
+          Q2[3 * ri + cj] = lo ? 0.0 : a0;
+          Q3[3 * ri + cj] = lo ? 0.0 : a1;
+        }
+    }
     double X0[9], X1[9], X2[9], X3[9], Ab[9], T[9];
     ld9(xch + moff(c, 0), X0);
     ld9s<RS>(rec + R_RE * RS, Ab);
