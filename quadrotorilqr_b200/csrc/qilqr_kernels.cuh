@@ -12,10 +12,15 @@
 //
 // Kernels
 //   k_cost_trajectory   ILQR::cost_trajectory      (ilqr.hh:89-95)
-//   k_backward          ILQR::backwards_pass       (ilqr.hh:97-147) + exit A of solve (:61-68)
+//   k_backward_t1       ILQR::backwards_pass       (ilqr.hh:97-147) + exit A of solve (:61-68), one thread
+//                       per problem, no structure assumptions: the independent cross-check of the production
+//                       backward pass (k_linearise + k_riccati_g4 in qilqr_backward_split.cuh)
 //   k_rollout           ILQR::forward_sim + cost   (ilqr.hh:149-172, 89-95) + Armijo test of
-//                       line_search (:182-189) + exit B of solve (:78-84)
-//   k_compact           ordered stream compaction of the active / searching problem lists
+//                       line_search (:182-189) + exit B of solve (:78-84); MODE_WIDE: parallel step sizes
+//   k_select_alpha      first step size that passes the Armijo test among the parallel candidates
+//   k_compact*          ordered stream compaction of the active / searching problem lists
+//   k_mpc_advance       plant step + warm-start shift of the receding-horizon loop
+//   k_pack / k_unpack   array-of-structs <-> structure-of-arrays
 // =============================================================================
 #pragma once
 #include "qilqr_device.cuh"
