@@ -297,7 +297,7 @@ def main():
     prob_iters, prob_rollouts, solver_iters = tot["problem_iterations"], tot["problem_rollouts"], tot["solver_iterations"]
     res = np.frombuffer(res_dev[0].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     converged = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
-    ls_failed = int(np.sum(res["status"] == 4))
+    ls_failed = int(np.sum(res["status"] >= 4))
     max_iter_hit = int(np.sum(res["status"] == 3))
 
     # One batch at a time on one handle (no pipelining): the latency of a single batch, and the place

@@ -57,8 +57,10 @@ typedef enum {
   QILQR_STATUS_CONVERGED_EXPECTED = 1, /* exit at ilqr.hh:66-68 (predicted reduction small) */
   QILQR_STATUS_CONVERGED_ACTUAL = 2,   /* exit at ilqr.hh:82-84 (actual reduction small)    */
   QILQR_STATUS_MAX_ITERS = 3,          /* loop bound, ilqr.hh:58,86                          */
-  QILQR_STATUS_LINE_SEARCH_FAILED = 4  /* the reference throws here, ilqr.hh:191-193; also
-                                          how NaN/Inf costs surface                          */
+  QILQR_STATUS_LINE_SEARCH_FAILED = 4, /* the reference throws here, ilqr.hh:191-193          */
+  QILQR_STATUS_NONFINITE = 5           /* same exit (the reference throws the same error), but the
+                                          last candidate cost was NaN/Inf: a numerical blow-up,
+                                          which makes every Armijo comparison false            */
 } qilqr_status_t;
 
 /* QuadrotorModel constructor arguments (quadrotor_model.hh:8-10). */

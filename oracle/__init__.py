@@ -26,6 +26,7 @@ STATUS_CONVERGED_EXPECTED = 1
 STATUS_CONVERGED_ACTUAL = 2
 STATUS_MAX_ITERS = 3
 STATUS_LINE_SEARCH_FAILED = 4
+STATUS_NONFINITE = 5
 
 
 class Config(C.Structure):

@@ -812,6 +812,7 @@ enum Status {  // how solve() ended (ilqr.hh:53-87)
   STATUS_CONVERGED_ACTUAL = 2,    // exit B, ilqr.hh:82-84
   STATUS_MAX_ITERS = 3,           // exit C, ilqr.hh:86
   STATUS_LINE_SEARCH_FAILED = 4,  // throw at ilqr.hh:191-193
+  STATUS_NONFINITE = 5,           // the same throw, reached because the last candidate cost was NaN/Inf
 };
 
 struct CostReductionTerms { double QuTk = 0, kTQuuk = 0; };  // ilqr.hh:13-16
@@ -856,6 +857,7 @@ struct ILQR {
   T dt_s_;
   ILQROptions options_;
   mutable int rollouts_ = 0;
+  mutable double last_line_search_cost_ = 0.0;
 
   // ilqr.hh:89-95
   T cost_trajectory(const Trajectory<T> &traj) const {
@@ -942,6 +944,7 @@ struct ILQR {
                              calculate_cost_reduction(terms, step);
       if (nc - cur_cost < desired) return {std::move(nt), nc, step};
       step *= options_.line_search_params.step_update;
+      last_line_search_cost_ = nc;
     }
     throw LineSearchFailure("Reached maximum number of line search iterations, " +
                             std::to_string(options_.line_search_params.max_iters) + "\n");
@@ -983,7 +986,7 @@ struct ILQR {
           new_cost = ls.cost;
           step = ls.step;
         } catch (const LineSearchFailure &) {
-          r.status = STATUS_LINE_SEARCH_FAILED;
+          r.status = std::isfinite(last_line_search_cost_) ? STATUS_LINE_SEARCH_FAILED : STATUS_NONFINITE;
           break;
         }
       }

@@ -373,7 +373,7 @@ struct ILQR {  // ilqr.hh:25-206
     qilqr_result_t res{};
     check(qilqr_solve_host(h_->h, 1, int(n), desired_.data(), 1, in.data(), out.data(), nullptr, nullptr, hist.data(),
                            cap, dbg.empty() ? nullptr : dbg.data(), cap, &res), h_->h);
-    if (res.status == QILQR_STATUS_LINE_SEARCH_FAILED)  // ilqr.hh:191-193
+    if (res.status == QILQR_STATUS_LINE_SEARCH_FAILED || res.status == QILQR_STATUS_NONFINITE)  // ilqr.hh:191-193
       throw std::runtime_error("Reached maximum number of line search iterations, " +
                                std::to_string(options_.line_search_params.max_iters) + "\n");
     ILQRDebug<ModelT> debug;

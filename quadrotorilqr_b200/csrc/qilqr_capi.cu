@@ -671,7 +671,7 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
       for (int b = 0; b < B; ++b) {
         acc[0] += res[b].backward_passes;
         acc[1] += res[b].rollouts;
-        acc[2] += (res[b].status == QILQR_STATUS_MAX_ITERS || res[b].status == QILQR_STATUS_LINE_SEARCH_FAILED);
+        acc[2] += (res[b].status == QILQR_STATUS_MAX_ITERS || res[b].status >= QILQR_STATUS_LINE_SEARCH_FAILED);
       }
       acc[3] += B;
     }
@@ -906,7 +906,7 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
   QCUDA(S, cudaMemcpyAsync(hstatus.data(), st.status, sizeof(int) * B, cudaMemcpyDeviceToHost, st_));
   QCUDA(S, cudaStreamSynchronize(st_));
   for (int b = 0; b < B; ++b) {
-    status[b] = (hstatus[b] == QILQR_STATUS_LINE_SEARCH_FAILED) ? QILQR_ERR_LINE_SEARCH : QILQR_OK;
+    status[b] = (hstatus[b] >= QILQR_STATUS_LINE_SEARCH_FAILED) ? QILQR_ERR_LINE_SEARCH : QILQR_OK;
     step[b] = halpha[b];
   }
   QCUDA(S, cudaGetLastError());

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
     const int ls = st.ls_iter[b] + 1;
     st.ls_iter[b] = ls;
     if (ls >= p.ls_max_iters) {
-      st.status[b] = QILQR_STATUS_LINE_SEARCH_FAILED;  // ilqr.hh:191-193
+      st.status[b] = isfinite(cost) ? QILQR_STATUS_LINE_SEARCH_FAILED : QILQR_STATUS_NONFINITE;  // ilqr.hh:191-193
       st.phase[b] = PHASE_DONE;
     }
   }
@@ -666,9 +666,11 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
   double alpha = st.alpha[b];
   const int ls0 = st.ls_iter[b];
   int ls = ls0;
+  bool last_finite = true;
   for (int j = 0; j < palpha; ++j) {
     if (ls >= p.ls_max_iters) break;
     const double cost = wide_cost[size_t(j) * B + b];
+    last_finite = isfinite(cost);
     const double desired = p.desired_reduction_frac * (alpha * qutk + alpha * alpha * ktq / 2.0);
     if (cost - cur_cost < desired) {
       st.alpha[b] = alpha;
@@ -684,7 +686,7 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
   st.alpha[b] = alpha;
   st.ls_iter[b] = ls;
   if (ls >= p.ls_max_iters) {
-    st.status[b] = QILQR_STATUS_LINE_SEARCH_FAILED;
+    st.status[b] = (last_finite) ? QILQR_STATUS_LINE_SEARCH_FAILED : QILQR_STATUS_NONFINITE;
     st.phase[b] = PHASE_DONE;
   }
 }

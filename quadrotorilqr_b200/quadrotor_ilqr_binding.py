@@ -35,7 +35,7 @@ class QuadrotorILQR:
                                hist_cap=int(np.ceil(self._options.convergence_criteria.max_iters)) + 1,
                                want_debug=self._options.populate_debug)
         res = r["results"][0]
-        if res["status"] == _capi.STATUS_LINE_SEARCH_FAILED:  # std::runtime_error, ilqr.hh:191-193
+        if res["status"] in (_capi.STATUS_LINE_SEARCH_FAILED, _capi.STATUS_NONFINITE):  # std::runtime_error, ilqr.hh:191-193
             raise RuntimeError("Reached maximum number of line search iterations, "
                                f"{self._options.line_search_params.max_iters}\n")
         nd = int(res["num_debug"]) if self._options.populate_debug else 0
