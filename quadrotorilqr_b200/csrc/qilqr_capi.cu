@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <atomic>
 #include <vector>
 
 #include "qilqr_api_kernels.cuh"
@@ -240,6 +241,7 @@ int wait_counts(qilqr_solver *S, cudaStream_t st) {
     }
     std::this_thread::yield();
   }
+  std::atomic_thread_fence(std::memory_order_acquire);  // the list lengths are read after the sequence word
   return QILQR_OK;
 }
 
