@@ -110,6 +110,19 @@ int qilqr_create(const qilqr_model_t *model, const double *Q /*[144]*/, const do
                  double dt_s, const qilqr_options_t *options, int device, qilqr_solver_t **out);
 void qilqr_destroy(qilqr_solver_t *solver);
 int qilqr_set_options(qilqr_solver_t *solver, const qilqr_options_t *options);
+
+/* The ModelT concept (ilqr.hh:25-44: ILQR<ModelT> sees only discrete_dynamics(x, u, dt, diffs*) with
+ * dense J_x, J_u, and minus()).  The reference ships one model; these flags select a second dynamics
+ * function on the same state manifold, solved by model-agnostic kernels that consume dense Jacobians
+ * (not in the reference; defined by QuadrotorModelVariant in oracle/qilqr_oracle.hpp):
+ *   QILQR_MODEL_RK4       RK4 over continuous_dynamics, the scheme commented out at
+ *                         quadrotor_model.cc:51-63, with the chain rule through its stages
+ *   QILQR_MODEL_CORIOLIS  adds the transport term -omega x v to the body linear acceleration
+ *   QILQR_MODEL_GENERIC   runs the model-agnostic kernels even for the reference model (cross-check:
+ *                         same results as the quadrotor-specific kernels to rounding)
+ * 0 (the default) is the reference's QuadrotorModel on the quadrotor-specific kernels. */
+enum { QILQR_MODEL_REFERENCE = 0, QILQR_MODEL_RK4 = 1, QILQR_MODEL_CORIOLIS = 2, QILQR_MODEL_GENERIC = 4 };
+int qilqr_set_model_variant(qilqr_solver_t *solver, int model_flags);
 const char *qilqr_error_string(int err);
 const char *qilqr_last_error_message(const qilqr_solver_t *solver);
 /* Number of this library's kernels launched by the solver so far (for bench.py's gpu_launches). */

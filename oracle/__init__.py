@@ -50,7 +50,7 @@ class Config(C.Structure):
         ("ls_max_iters", C.c_int32),
         ("populate_debug", C.c_int32),
         ("symmetrize_vxx", C.c_int32),
-        ("reserved", C.c_int32),
+        ("model_kind", C.c_int32),
     ]
 
 
@@ -111,7 +111,7 @@ def _in(a, shape=None):
 def make_config(mass_kg=1.0, inertia=None, arm_length_m=1.0, torque_to_thrust_ratio_m=0.0,
                 g_mpss=9.81, Q=None, R=None, dt_s=0.1, step_update=0.5, desired_reduction_frac=0.5,
                 ls_max_iters=100, rtol=1e-12, atol=1e-12, max_iters=100.0, populate_debug=False,
-                symmetrize_vxx=False, quu_regularization=0.0) -> Config:
+                symmetrize_vxx=False, quu_regularization=0.0, model_kind=0) -> Config:
     c = Config()
     c.mass_kg = mass_kg
     c.inertia[:] = _in(np.eye(3) if inertia is None else inertia, (9,)).tolist()
@@ -130,6 +130,7 @@ def make_config(mass_kg=1.0, inertia=None, arm_length_m=1.0, torque_to_thrust_ra
     c.populate_debug = int(bool(populate_debug))
     c.symmetrize_vxx = int(bool(symmetrize_vxx))
     c.quu_regularization = quu_regularization
+    c.model_kind = int(model_kind)  # bit 0: RK4 integrator, bit 1: Coriolis term (QuadrotorModelVariant)
     return c
 
 

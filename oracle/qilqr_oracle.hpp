@@ -746,6 +746,88 @@ struct QuadrotorModel {
 };
 
 // ----------------------------------------------------------------------------
+// A SECOND MODEL for the ModelT concept of ilqr.hh:25-44 -- NOT in the reference.
+// ILQR<ModelT> only needs State/Control, discrete_dynamics(x, u, dt, diffs*) and the
+// free minus(); this variant keeps the quadrotor's state manifold and changes the
+// dynamics function, to check that the CUDA solver is not hard-wired to one of them
+// (SURVEY.md section 8(f)-4):
+//   integrator_ = 1  classical RK4 over continuous_dynamics, the scheme of the block the
+//                    reference left commented out (quadrotor_model.cc:51-63): stage states
+//                    x (+) dt_i k_{i-1} with dt_i = {0, dt/2, dt/2, dt}, weights
+//                    {1/6, 2/6, 2/6, 1/6} (doubles here; the comment holds them as floats),
+//                    then x+ = x (+) dt xdot.  The differentials are the chain rule through
+//                    the four stages (the reference never wrote them).
+//   coriolis_ = true adds the transport term -omega x v to the body-frame linear acceleration,
+//                    which quadrotor_model.cc:65-78 leaves out.
+// integrator_ = 0, coriolis_ = false reproduces QuadrotorModel exactly.
+// There is no reference behaviour to pin this model against: the oracle IS its definition
+// (finite differences check its Jacobians in tests/test_model_variants.py).
+// ----------------------------------------------------------------------------
+template <class T>
+struct QuadrotorModelVariant {
+  QuadrotorModel<T> base_;
+  int integrator_ = 0;
+  bool coriolis_ = false;
+
+  StateTangent<T> continuous_dynamics(const State<T> &x, const Control<T> &u,
+                                      DynamicsDifferentials<T> *diffs = nullptr) const {
+    StateTangent<T> xdot = base_.continuous_dynamics(x, u, diffs);
+    if (coriolis_) {
+      const Vec3<T> v = lin(x.body_velocity), w = ang(x.body_velocity);
+      const Vec3<T> transport = hat(v) * w;  // v x omega = -(omega x v)
+      for (int i = 0; i < 3; ++i) xdot.body_acceleration[i] = xdot.body_acceleration[i] + transport[i];
+      if (diffs) {
+        diffs->J_x.template set_block<3, 3>(6, 6, -hat(w));
+        diffs->J_x.template set_block<3, 3>(6, 9, hat(v));
+      }
+    }
+    return xdot;
+  }
+
+  State<T> discrete_dynamics(const State<T> &x, const Control<T> &u, const T &dt_s,
+                             DynamicsDifferentials<T> *diffs = nullptr) const {
+    if (integrator_ == 0) {  // quadrotor_model.cc:33-49
+      const StateTangent<T> x_dot = continuous_dynamics(x, u, diffs);
+      BinaryStateFuncDiffs<T> euler_diffs;
+      const State<T> x_next = euler_step(x, x_dot, dt_s, diffs ? &euler_diffs : nullptr);
+      if (diffs) {
+        diffs->J_x = euler_diffs.J_x_lhs + euler_diffs.J_x_rhs * diffs->J_x;
+        diffs->J_u = euler_diffs.J_x_rhs * diffs->J_u;
+      }
+      return x_next;
+    }
+    const T coeffs[4] = {T(1.0) / T(6.0), T(2.0) / T(6.0), T(2.0) / T(6.0), T(1.0) / T(6.0)};
+    const T half_dt_s = dt_s / T(2.0);
+    const T dt_table[4] = {T(0.0), half_dt_s, half_dt_s, dt_s};
+    StateTangent<T> k{Vec6<T>::Zero(), Vec6<T>::Zero()};
+    Vec12<T> x_dot = Vec12<T>::Zero();
+    StateJacobian<T> dk_dx = StateJacobian<T>::Zero(), dxdot_dx = StateJacobian<T>::Zero();
+    ControlJacobian<T> dk_du = ControlJacobian<T>::Zero(), dxdot_du = ControlJacobian<T>::Zero();
+    for (int i = 0; i < 4; ++i) {
+      BinaryStateFuncDiffs<T> e;
+      const State<T> xi = euler_step(x, k, dt_table[i], diffs ? &e : nullptr);
+      DynamicsDifferentials<T> f;
+      k = continuous_dynamics(xi, u, diffs ? &f : nullptr);
+      x_dot = x_dot + coeffs[i] * k.coeffs();
+      if (diffs) {
+        dk_du = f.J_x * (e.J_x_rhs * dk_du) + f.J_u;
+        dk_dx = f.J_x * (e.J_x_lhs + e.J_x_rhs * dk_dx);
+        dxdot_dx = dxdot_dx + coeffs[i] * dk_dx;
+        dxdot_du = dxdot_du + coeffs[i] * dk_du;
+      }
+    }
+    BinaryStateFuncDiffs<T> e;
+    const State<T> x_next =
+        euler_step(x, StateTangent<T>::from_coeffs(x_dot), dt_s, diffs ? &e : nullptr);
+    if (diffs) {
+      diffs->J_x = e.J_x_lhs + e.J_x_rhs * dxdot_dx;
+      diffs->J_u = e.J_x_rhs * dxdot_du;
+    }
+    return x_next;
+  }
+};
+
+// ----------------------------------------------------------------------------
 // Trajectory (src/trajectory.hh:9-24), CostFunction (src/cost.hh)
 // ----------------------------------------------------------------------------
 template <class T>
@@ -850,9 +932,9 @@ struct SolveResult {
   double final_cost = 0;
 };
 
-template <class T>
+template <class T, class ModelT = QuadrotorModel<T>>
 struct ILQR {
-  QuadrotorModel<T> model_;
+  ModelT model_;
   CostFunction<T> cost_function_;
   T dt_s_;
   ILQROptions options_;

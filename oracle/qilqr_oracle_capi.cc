@@ -34,7 +34,7 @@ typedef struct {
   int32_t ls_max_iters;
   int32_t populate_debug;
   int32_t symmetrize_vxx;
-  int32_t reserved;
+  int32_t model_kind;  // 0: the reference's QuadrotorModel; bit 0: RK4 integrator, bit 1: Coriolis term (QuadrotorModelVariant)
 } qoracle_config_t;
 }
 
@@ -119,6 +119,27 @@ ILQR<T> make_ilqr(const qoracle_config_t *c, const double *desired, int n) {
                  T(c->dt_s), make_options(c)};
 }
 template <class T>
+QuadrotorModelVariant<T> make_variant(const qoracle_config_t *c) {
+  return QuadrotorModelVariant<T>{make_model<T>(c), c->model_kind & 1, (c->model_kind & 2) != 0};
+}
+// f(solver) with the ILQR<ModelT> instantiation the configuration asks for
+template <class T, class F>
+void with_ilqr(const qoracle_config_t *c, const double *desired, int n, F &&f) {
+  if (c->model_kind == 0) {
+    f(make_ilqr<T>(c, desired, n));
+  } else {
+    f(ILQR<T, QuadrotorModelVariant<T>>{make_variant<T>(c),
+                                        CostFunction<T>{load_mat<T, 12, 12>(c->Q), load_mat<T, 4, 4>(c->R),
+                                                        load_traj<T>(desired, n)},
+                                        T(c->dt_s), make_options(c)});
+  }
+}
+template <class T, class F>
+void with_model(const qoracle_config_t *c, F &&f) {
+  if (c->model_kind == 0) f(make_model<T>(c));
+  else f(make_variant<T>(c));
+}
+template <class T>
 ControlUpdateTrajectory<T> load_update(const double *k, const double *K, int n) {
   ControlUpdateTrajectory<T> u(n);
   for (int i = 0; i < n; ++i) {
@@ -185,26 +206,28 @@ int qoracle_check_model(const qoracle_config_t *c) {
 int qoracle_continuous_dynamics(const qoracle_config_t *c, const double *x, const double *u,
                                 double *xdot, double *J_x, double *J_u) {
   try {
-    const auto m = make_model<double>(c);
-    DynamicsDifferentials<double> d;
-    const auto r = m.continuous_dynamics(load_state<double>(x), load_mat<double, 4, 1>(u),
-                                         (J_x || J_u) ? &d : nullptr);
-    store_mat(r.coeffs(), xdot);
-    if (J_x) store_mat(d.J_x, J_x);
-    if (J_u) store_mat(d.J_u, J_u);
+    with_model<double>(c, [&](const auto &m) {
+      DynamicsDifferentials<double> d;
+      const auto r = m.continuous_dynamics(load_state<double>(x), load_mat<double, 4, 1>(u),
+                                           (J_x || J_u) ? &d : nullptr);
+      store_mat(r.coeffs(), xdot);
+      if (J_x) store_mat(d.J_x, J_x);
+      if (J_u) store_mat(d.J_u, J_u);
+    });
   } catch (const std::runtime_error &) { return 1; }
   return 0;
 }
 int qoracle_discrete_dynamics(const qoracle_config_t *c, const double *x, const double *u,
                               double dt_s, double *x_next, double *J_x, double *J_u) {
   try {
-    const auto m = make_model<double>(c);
-    DynamicsDifferentials<double> d;
-    const auto r = m.discrete_dynamics(load_state<double>(x), load_mat<double, 4, 1>(u), dt_s,
-                                       (J_x || J_u) ? &d : nullptr);
-    store_state(r, x_next);
-    if (J_x) store_mat(d.J_x, J_x);
-    if (J_u) store_mat(d.J_u, J_u);
+    with_model<double>(c, [&](const auto &m) {
+      DynamicsDifferentials<double> d;
+      const auto r = m.discrete_dynamics(load_state<double>(x), load_mat<double, 4, 1>(u), dt_s,
+                                         (J_x || J_u) ? &d : nullptr);
+      store_state(r, x_next);
+      if (J_x) store_mat(d.J_x, J_x);
+      if (J_u) store_mat(d.J_u, J_u);
+    });
   } catch (const std::runtime_error &) { return 1; }
   return 0;
 }
@@ -254,8 +277,9 @@ double qoracle_cost(const qoracle_config_t *c, const double *x, const double *u,
 int qoracle_forward_sim(const qoracle_config_t *c, int n, const double *desired, const double *cur,
                         const double *k, const double *K, double alpha, double *out) {
   try {
-    const auto s = make_ilqr<double>(c, desired, n);
-    store_traj(s.forward_sim(load_traj<double>(cur, n), load_update<double>(k, K, n), alpha), out);
+    with_ilqr<double>(c, desired, n, [&](const auto &s) {
+      store_traj(s.forward_sim(load_traj<double>(cur, n), load_update<double>(k, K, n), alpha), out);
+    });
   } catch (const std::exception &) { return 1; }
   return 0;
 }
@@ -271,11 +295,12 @@ int qoracle_cost_trajectory(const qoracle_config_t *c, int n_desired, const doub
 int qoracle_backwards_pass(const qoracle_config_t *c, int n, const double *desired, const double *traj,
                            double *k, double *K, double *QuTk, double *kTQuuk) {
   try {
-    const auto s = make_ilqr<double>(c, desired, n);
-    auto [upd, terms] = s.backwards_pass(load_traj<double>(traj, n));
-    store_update(upd, k, K);
-    *QuTk = terms.QuTk;
-    *kTQuuk = terms.kTQuuk;
+    with_ilqr<double>(c, desired, n, [&](const auto &s) {
+      auto [upd, terms] = s.backwards_pass(load_traj<double>(traj, n));
+      store_update(upd, k, K);
+      *QuTk = terms.QuTk;
+      *kTQuuk = terms.kTQuuk;
+    });
   } catch (const std::exception &) { return 1; }
   return 0;
 }
@@ -284,12 +309,13 @@ int qoracle_line_search(const qoracle_config_t *c, int n, const double *desired,
                         double cur_cost, const double *k, const double *K, double QuTk, double kTQuuk,
                         double *out, double *new_cost, double *step) {
   try {
-    const auto s = make_ilqr<double>(c, desired, n);
-    CostReductionTerms t{QuTk, kTQuuk};
-    auto r = s.line_search(load_traj<double>(cur, n), cur_cost, load_update<double>(k, K, n), t);
-    store_traj(r.traj, out);
-    *new_cost = r.cost;
-    *step = r.step;
+    with_ilqr<double>(c, desired, n, [&](const auto &s) {
+      CostReductionTerms t{QuTk, kTQuuk};
+      auto r = s.line_search(load_traj<double>(cur, n), cur_cost, load_update<double>(k, K, n), t);
+      store_traj(r.traj, out);
+      *new_cost = r.cost;
+      *step = r.step;
+    });
   } catch (const LineSearchFailure &) { return 4; }
   catch (const std::exception &) { return 1; }
   return 0;
@@ -310,21 +336,22 @@ int qoracle_solve(const qoracle_config_t *c, int n, const double *desired, const
                   double *out_traj, double *out_k, double *out_K, double *cost_hist, double *step_hist,
                   double *debug_traj, qoracle_result_t *res) {
   try {
-    const auto s = make_ilqr<double>(c, desired, n);
-    const auto r = s.solve(load_traj<double>(initial, n));
-    store_traj(r.traj, out_traj);
-    store_update(r.last_update, out_k, out_K);
-    for (size_t i = 0; i < r.cost_history.size(); ++i) {
-      if (cost_hist) cost_hist[i] = r.cost_history[i];
-      if (step_hist) step_hist[i] = r.step_history[i];
-    }
-    if (debug_traj)
-      for (size_t i = 0; i < r.debug.size(); ++i) store_traj(r.debug[i].trajectory, debug_traj + i * n * 18);
-    res->status = r.status;
-    res->backward_passes = r.backward_passes;
-    res->rollouts = r.rollouts;
-    res->num_debug = int(r.cost_history.size());
-    res->final_cost = r.final_cost;
+    with_ilqr<double>(c, desired, n, [&](const auto &s) {
+      const auto r = s.solve(load_traj<double>(initial, n));
+      store_traj(r.traj, out_traj);
+      store_update(r.last_update, out_k, out_K);
+      for (size_t i = 0; i < r.cost_history.size(); ++i) {
+        if (cost_hist) cost_hist[i] = r.cost_history[i];
+        if (step_hist) step_hist[i] = r.step_history[i];
+      }
+      if (debug_traj)
+        for (size_t i = 0; i < r.debug.size(); ++i) store_traj(r.debug[i].trajectory, debug_traj + i * n * 18);
+      res->status = r.status;
+      res->backward_passes = r.backward_passes;
+      res->rollouts = r.rollouts;
+      res->num_debug = int(r.cost_history.size());
+      res->final_cost = r.final_cost;
+    });
   } catch (const std::exception &) { return 1; }
   return 0;
 }
@@ -370,7 +397,7 @@ int qoracle_solve_batch(const qoracle_config_t *c, int batch, int n, const doubl
 int qoracle_count_flops(const qoracle_config_t *c, int n, const double *desired, const double *traj,
                         double *out) {
   try {
-    const auto s = make_ilqr<CountedDouble>(c, desired, n);
+    with_ilqr<CountedDouble>(c, desired, n, [&](const auto &s) {
     const auto tr = load_traj<CountedDouble>(traj, n);
     FlopCounter::reset();
     auto [upd, terms] = s.backwards_pass(tr);
@@ -390,6 +417,7 @@ int qoracle_count_flops(const qoracle_config_t *c, int n, const double *desired,
     }
     out[3] = double(FlopCounter::total()) / n + 1;  // + the running sum
     FlopCounter::reset();
+    });
   } catch (const std::exception &) { return 1; }
   return 0;
 }

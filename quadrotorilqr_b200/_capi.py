@@ -89,7 +89,13 @@ EXPORTED_SYMBOLS = [
     "qilqr_unpack_trajectory_device", "qilqr_rollout_constant_control_device",
     "qilqr_last_solve_stats", "qilqr_set_profiling", "qilqr_measure_fp64_peak",
     "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
+    "qilqr_set_model_variant",
 ]
+
+MODEL_REFERENCE = 0
+MODEL_RK4 = 1
+MODEL_CORIOLIS = 2
+MODEL_GENERIC = 4
 
 
 def build(force: bool = False) -> str:

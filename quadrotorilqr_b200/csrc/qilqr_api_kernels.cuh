@@ -7,6 +7,7 @@
 // =============================================================================
 #pragma once
 #include "qilqr_device.cuh"
+#include "qilqr_model_generic.cuh"
 
 namespace qilqr {
 
@@ -26,20 +27,29 @@ __global__ void k_api_continuous_dynamics(const __grid_constant__ DeviceParams p
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const double *xs = x + size_t(b) * 13, *us = u + size_t(b) * 4;
-  double R[9], acc[6];
-  quat_to_rot(xs + 3, R);
-  body_acceleration(p, R, xs + 7, us, acc);
   double *o = xdot + size_t(b) * 12;
-  for (int i = 0; i < 6; ++i) { o[i] = xs[7 + i]; o[6 + i] = acc[i]; }
-  if (J_x) {
-    double *J = J_x + size_t(b) * 144;
-    zero_fill(J, 144);
-    for (int i = 0; i < 6; ++i) J[i * 12 + 6 + i] = 1.0;
-    double gz[3], Wc[9];
-    continuous_blocks(p, xs + 3, xs + 7, gz, Wc);
-    const double G[9] = {0.0, -gz[2], gz[1], gz[2], 0.0, -gz[0], -gz[1], gz[0], 0.0};
-    put_block(J, 12, 6, 3, G);
-    put_block(J, 12, 9, 9, Wc);
+  if (p.coriolis) {  // model variant (qilqr_model_generic.cuh)
+    double xl[13], k[12];
+    for (int i = 0; i < 13; ++i) xl[i] = xs[i];
+    gm::ContBlocks F;
+    gm::continuous_with_blocks(p, xl, us, k, F);
+    for (int i = 0; i < 12; ++i) o[i] = k[i];
+    if (J_x) gm::cont_jx_dense(p, F, J_x + size_t(b) * 144);
+  } else {
+    double R[9], acc[6];
+    quat_to_rot(xs + 3, R);
+    body_acceleration(p, R, xs + 7, us, acc);
+    for (int i = 0; i < 6; ++i) { o[i] = xs[7 + i]; o[6 + i] = acc[i]; }
+    if (J_x) {
+      double *J = J_x + size_t(b) * 144;
+      zero_fill(J, 144);
+      for (int i = 0; i < 6; ++i) J[i * 12 + 6 + i] = 1.0;
+      double gz[3], Wc[9];
+      continuous_blocks(p, xs + 3, xs + 7, gz, Wc);
+      const double G[9] = {0.0, -gz[2], gz[1], gz[2], 0.0, -gz[0], -gz[1], gz[0], 0.0};
+      put_block(J, 12, 6, 3, G);
+      put_block(J, 12, 9, 9, Wc);
+    }
   }
   if (J_u) {
     double *J = J_u + size_t(b) * 48;
@@ -56,6 +66,16 @@ __global__ void k_api_discrete_dynamics(const __grid_constant__ DeviceParams p, 
   double xs[13], us[4];
   for (int i = 0; i < 13; ++i) xs[i] = x[size_t(b) * 13 + i];
   for (int i = 0; i < 4; ++i) us[i] = u[size_t(b) * 4 + i];
+  if (p.integrator || p.coriolis) {  // model variant (qilqr_model_generic.cuh)
+    if (J_x || J_u) {
+      double xn[13];
+      gm::discrete_with_jacobians(p, xs, us, xn, J_x ? J_x + size_t(b) * 144 : nullptr,
+                                  J_u ? J_u + size_t(b) * 48 : nullptr, 1);
+    }
+    gm::discrete_step_any(p, xs, us);
+    for (int i = 0; i < 13; ++i) x_next[size_t(b) * 13 + i] = xs[i];
+    return;
+  }
   if (J_x) {
     ABlocks A;
     dynamics_blocks(p, xs + 3, xs + 7, A);

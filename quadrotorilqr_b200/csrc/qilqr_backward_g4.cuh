@@ -74,23 +74,21 @@ QD void m3_madd_hat(const double *M, const double *w, double *C) {
   }
 }
 
-// Linearise one knot into a record whose element e lives at rec[e * RS].  DENSEQ = false requires
-// Q_pv = Q_vp = 0 (100-double record); DENSEQ = true handles any Q (172-double record).
-template <int RS = 1, bool DENSEQ = false>
-QD void linearise_to_record(const DeviceParams &p, const double *x, const double *u, const double *xd,
-                            const double *ud, double *rec) {
-  {
-    ABlocks A;
-    dynamics_blocks(p, x + 3, x + 7, A);
-    st9s<RS>(rec + R_RE * RS, A.Re);
-    st9s<RS>(rec + R_TE * RS, A.Te);
-    st9s<RS>(rec + R_DJR * RS, A.dJr);
-    st9s<RS>(rec + R_DQB * RS, A.dQb);
-    rec[(R_GZ + 0) * RS] = A.dG[7];
-    rec[(R_GZ + 1) * RS] = A.dG[2];
-    rec[(R_GZ + 2) * RS] = A.dG[3];
-    st9s<RS>(rec + R_WD * RS, A.Wd);
-  }
+// Where the cost differentials of one knot go inside a record (element index; the element lives at
+// rec[index * RS]): C.x, C.u, and the pose/pose, pose/velocity, velocity/pose 6x6 blocks of C.xx.
+struct G4Layout {
+  __host__ __device__ static constexpr int cx(int j) { return R_CX + j; }
+  __host__ __device__ static constexpr int cu(int j) { return R_CU + j; }
+  __host__ __device__ static constexpr int cpp(int i, int j) { return R_CPP + 6 * i + j; }
+  __host__ __device__ static constexpr int cpv(int i, int j) { return R_CPV + 6 * i + j; }
+  __host__ __device__ static constexpr int cvp(int i, int j) { return R_CVP + 6 * i + j; }
+};
+
+// CostFunction differentials (cost.hh:47-57) of one knot into a record.  DENSEQ = false requires
+// Q_pv = Q_vp = 0 and writes only C.x, C.u and the pose block of C.xx; DENSEQ = true handles any Q.
+template <int RS, bool DENSEQ, class L>
+QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, const double *xd,
+                       const double *ud, double *rec) {
   double dx[12], Jli[9], Ji[9], Qi[9];
   Angle ang;
   state_minus(x, xd, dx, Jli, &ang);
@@ -123,13 +121,13 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
   m3T_vec(Qi, y, Cx + 3);
   m3T_vec_add(Ji, y + 3, Cx + 3);
 #pragma unroll
-  for (int j = 0; j < 6; ++j) { rec[(R_CX + j) * RS] = Cx[j]; rec[(R_CX + 6 + j) * RS] = y[6 + j]; }
+  for (int j = 0; j < 6; ++j) { rec[L::cx(j) * RS] = Cx[j]; rec[L::cx(6 + j) * RS] = y[6 + j]; }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double s = (2.0 * (u[0] - ud[0])) * p.R[j];
 #pragma unroll
     for (int l = 1; l < 4; ++l) s = fma(2.0 * (u[l] - ud[l]), p.R[4 * l + j], s);
-    rec[(R_CU + j) * RS] = s;
+    rec[L::cu(j) * RS] = s;
   }
   // C_xx = ((2 J^T) Q) J with J = blkdiag(J6, I), J6 = [[Ji, Qi], [0, Ji]]:
   //   rows 0..5 of P = (2 J^T) Q are (2 J6^T) Q[0:6, :];  C_pp = P[:, 0:6] J6,  C_pv = P[:, 6:12]
@@ -148,24 +146,24 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      rec[(R_CPP + 6 * i + j) * RS] = fma(Pa[2], Ji[6 + j], fma(Pa[1], Ji[3 + j], Pa[0] * Ji[j]));
-      rec[(R_CPP + 6 * (3 + i) + j) * RS] = fma(Pb[2], Ji[6 + j], fma(Pb[1], Ji[3 + j], Pb[0] * Ji[j]));
+      rec[L::cpp(i, j) * RS] = fma(Pa[2], Ji[6 + j], fma(Pa[1], Ji[3 + j], Pa[0] * Ji[j]));
+      rec[L::cpp(3 + i, j) * RS] = fma(Pb[2], Ji[6 + j], fma(Pb[1], Ji[3 + j], Pb[0] * Ji[j]));
       double s = fma(Pa[2], Qi[6 + j], fma(Pa[1], Qi[3 + j], Pa[0] * Qi[j]));
       s = fma(Pa[3], Ji[j], s);
       s = fma(Pa[4], Ji[3 + j], s);
       s = fma(Pa[5], Ji[6 + j], s);
-      rec[(R_CPP + 6 * i + 3 + j) * RS] = s;
+      rec[L::cpp(i, 3 + j) * RS] = s;
       double s2 = fma(Pb[2], Qi[6 + j], fma(Pb[1], Qi[3 + j], Pb[0] * Qi[j]));
       s2 = fma(Pb[3], Ji[j], s2);
       s2 = fma(Pb[4], Ji[3 + j], s2);
       s2 = fma(Pb[5], Ji[6 + j], s2);
-      rec[(R_CPP + 6 * (3 + i) + 3 + j) * RS] = s2;
+      rec[L::cpp(3 + i, 3 + j) * RS] = s2;
     }
     if (DENSEQ) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        rec[(R_CPV + 6 * i + j) * RS] = Pa[6 + (DENSEQ ? j : 0)];
-        rec[(R_CPV + 6 * (3 + i) + j) * RS] = Pb[6 + (DENSEQ ? j : 0)];
+        rec[L::cpv(i, j) * RS] = Pa[6 + (DENSEQ ? j : 0)];
+        rec[L::cpv(3 + i, j) * RS] = Pb[6 + (DENSEQ ? j : 0)];
       }
     }
   }
@@ -178,15 +176,35 @@ QD void linearise_to_record(const DeviceParams &p, const double *x, const double
       for (int k = 0; k < 6; ++k) Pr[k] = 2.0 * p.Q[12 * (6 + i) + k];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        rec[(R_CVP + 6 * i + j) * RS] = fma(Pr[2], Ji[6 + j], fma(Pr[1], Ji[3 + j], Pr[0] * Ji[j]));
+        rec[L::cvp(i, j) * RS] = fma(Pr[2], Ji[6 + j], fma(Pr[1], Ji[3 + j], Pr[0] * Ji[j]));
         double s = fma(Pr[2], Qi[6 + j], fma(Pr[1], Qi[3 + j], Pr[0] * Qi[j]));
         s = fma(Pr[3], Ji[j], s);
         s = fma(Pr[4], Ji[3 + j], s);
         s = fma(Pr[5], Ji[6 + j], s);
-        rec[(R_CVP + 6 * i + 3 + j) * RS] = s;
+        rec[L::cvp(i, 3 + j) * RS] = s;
       }
     }
   }
+}
+
+// Linearise one knot into a record whose element e lives at rec[e * RS].  DENSEQ = false requires
+// Q_pv = Q_vp = 0 (100-double record); DENSEQ = true handles any Q (172-double record).
+template <int RS = 1, bool DENSEQ = false>
+QD void linearise_to_record(const DeviceParams &p, const double *x, const double *u, const double *xd,
+                            const double *ud, double *rec) {
+  {
+    ABlocks A;
+    dynamics_blocks(p, x + 3, x + 7, A);
+    st9s<RS>(rec + R_RE * RS, A.Re);
+    st9s<RS>(rec + R_TE * RS, A.Te);
+    st9s<RS>(rec + R_DJR * RS, A.dJr);
+    st9s<RS>(rec + R_DQB * RS, A.dQb);
+    rec[(R_GZ + 0) * RS] = A.dG[7];
+    rec[(R_GZ + 1) * RS] = A.dG[2];
+    rec[(R_GZ + 2) * RS] = A.dG[3];
+    st9s<RS>(rec + R_WD * RS, A.Wd);
+  }
+  cost_to_record<RS, DENSEQ, G4Layout>(p, x, u, xd, ud, rec);
 }
 }  // namespace g4
 

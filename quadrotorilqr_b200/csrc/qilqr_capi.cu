@@ -20,6 +20,7 @@
 #include "qilqr_kernels.cuh"
 #include "qilqr_backward_g4.cuh"
 #include "qilqr_backward_split.cuh"
+#include "qilqr_backward_dense.cuh"
 
 using namespace qilqr;
 
@@ -71,6 +72,7 @@ struct qilqr_solver {
   int g4_kpp = 4;                // knots linearised per phase by the quad kernel (1, 2 or 4)
   bool force_t1 = false;         // QILQR_BACKWARD=t1: the one-thread-per-problem kernel (cross-checks)
   bool split_backward = true;    // linearise kernel + TMA-fed Riccati kernel (default) vs the fused quad kernel
+  bool generic_path = false;     // model-agnostic kernels (dense J_x, J_u): any model variant, or forced for cross-checks
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
 
@@ -278,7 +280,35 @@ int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   ++S->launches;
   return QILQR_OK;
 }
+// The model-agnostic backward pass: dense records from the configured model, dense Riccati sweep.
+int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
+  const int n8 = (ba.n + 7) & ~7;
+  const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * dn::DREC;
+  if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
+  const size_t smem = sizeof(double) * dn::smem_doubles();
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const size_t threads = size_t(n8) * ba.pr.N;
+  k_linearise_dense<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  k_riccati_dense<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  ++S->launches;
+  return QILQR_OK;
+}
+// forward_sim (+ cost, + line-search bookkeeping) with the dynamics of the configured model
+void launch_rollout(qilqr_solver *S, const RolloutArgs &ra, int threads, cudaStream_t st) {
+  if (S->generic_path) k_rollout<true><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
+  else k_rollout<false><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
+}
 int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
+  if (S->generic_path) {
+    const int rc = launch_dense(S, ba);
+    if (rc) return fail(S, rc, "out of device memory for the linearisation records");
+    return QILQR_OK;
+  }
   if (S->split_backward && !S->force_t1) {
     const int rc = S->q_block_diagonal ? launch_split<false>(S, ba) : launch_split<true>(S, ba);
     if (rc) return fail(S, rc, "out of device memory for the linearisation records");
@@ -359,7 +389,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       RolloutArgs ra{pr, st, list, n, i, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1};
       {
         SpanGuard g(S, 1);
-        k_rollout<<<blocks_for(n, 128), 128, 0, st_>>>(S->p, ra);
+        launch_rollout(S, ra, n, st_);
       }
       S->stats.rollout_problem_knots += int64_t(n) * N;
       S->stats.problem_rollouts += n;
@@ -399,7 +429,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         RolloutArgs rw{pr, st, listS[s], n_wide, i, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha};
         {
           SpanGuard g(S, 1);
-          k_rollout<<<blocks_for(n_wide * P_alpha, 128), 128, 0, st_>>>(S->p, rw);
+          launch_rollout(S, rw, n_wide * P_alpha, st_);
         }
         S->stats.rollout_problem_knots += int64_t(n_wide) * P_alpha * N;
         k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B, S->wide_d.as<double>(), P_alpha);
@@ -578,6 +608,13 @@ int qilqr_set_options(qilqr_solver_t *S, const qilqr_options_t *options) {
   if (!S || !options) return QILQR_ERR_INVALID_ARGUMENT;
   S->opt = *options;
   apply_options(S);
+  return QILQR_OK;
+}
+int qilqr_set_model_variant(qilqr_solver_t *S, int model_flags) {
+  if (!S || model_flags < 0 || model_flags > 7) return QILQR_ERR_INVALID_ARGUMENT;
+  S->p.integrator = (model_flags & QILQR_MODEL_RK4) ? 1 : 0;
+  S->p.coriolis = (model_flags & QILQR_MODEL_CORIOLIS) ? 1 : 0;
+  S->generic_path = model_flags != 0;
   return QILQR_OK;
 }
 const char *qilqr_last_error_message(const qilqr_solver_t *S) { return S ? S->last_error.c_str() : ""; }
@@ -783,7 +820,7 @@ int qilqr_forward_sim_host(qilqr_solver_t *S, int B, int N, const double *curren
   Problem pr{B, N, 1, nullptr, nullptr, nullptr, S->gk.as<double>(), S->gK.as<double>()};
   RolloutArgs ra{pr, SolveState{}, nullptr, B, 0, MODE_FORWARD, S->traj_soa.as<double>(), S->buf1.as<double>(),
                  S->misc.as<double>(), nullptr, 1};
-  k_rollout<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, ra);
+  launch_rollout(S, ra, B, st_);
   ++S->launches;
   unpack_traj(S, B, N, S->buf1.as<double>(), S->stage_a.as<double>());
   QCUDA(S, cudaMemcpyAsync(out_traj, S->stage_a.ptr, sizeof(double) * size_t(B) * N * 18, cudaMemcpyDeviceToHost, st_));
@@ -887,7 +924,7 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
   int n_search = B, s = 0;
   while (n_search > 0) {
     RolloutArgs ra{pr, st, search, n_search, 1, MODE_LINE_SEARCH, nullptr, nullptr, nullptr, nullptr, 1};
-    k_rollout<<<blocks_for(n_search, 128), 128, 0, st_>>>(S->p, ra);
+    launch_rollout(S, ra, n_search, st_);
     // phase: rejected problems keep PHASE_ACTIVE(0)... mark searching ones explicitly below
     k_compact<<<1, 1024, 0, st_>>>(search, n_search, st.phase, dummy, listS[s], S->d_counts);
     S->launches += 2;

@@ -36,6 +36,9 @@ struct DeviceParams {
   double step_update, desired_reduction_frac, rtol, atol, max_iters, quu_reg;
   int ls_max_iters;
   int symmetrize_vxx;
+  // model variant behind the ModelT concept (qilqr_model_generic.cuh); 0/0 = the reference's QuadrotorModel
+  int integrator;  // 0: explicit Euler (quadrotor_model.cc:33-49), 1: RK4 (the scheme commented out at :51-63)
+  int coriolis;    // 1: adds -omega x v to the body linear acceleration
 };
 
 // ---------------------------------------------------------------------------

@@ -24,6 +24,7 @@
 // =============================================================================
 #pragma once
 #include "qilqr_device.cuh"
+#include "qilqr_model_generic.cuh"
 #include "../../include/qilqr.h"
 
 namespace qilqr {
@@ -130,6 +131,8 @@ struct RolloutArgs {
 #ifndef QILQR_ROLLOUT_MINB
 #define QILQR_ROLLOUT_MINB 2
 #endif
+// GENERIC = false: the reference's QuadrotorModel, inlined; true: any model variant (qilqr_model_generic.cuh)
+template <bool GENERIC>
 __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int wide_j = (a.mode == MODE_WIDE) ? tid / a.n : 0;  // j-major so that a warp covers consecutive problems
@@ -190,7 +193,9 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
       for (int j = 0; j < 4; ++j) du[j] = u[j] - ud[j];
       cost = cost + quadratic_cost(p, dx, du);
     }
-    discrete_step(p, x, x + 3, x + 7, u);  // also after the last knot, as ilqr.hh:168 does; result unused
+    // also after the last knot, as ilqr.hh:168 does; result unused
+    if (GENERIC) gm::discrete_step_any(p, x, u);
+    else discrete_step(p, x, x + 3, x + 7, u);
   }
 
   if (a.mode == MODE_FORWARD) {
@@ -969,7 +974,7 @@ k_mpc_advance(const __grid_constant__ DeviceParams p, double *traj, double *plan
   for (int c = 0; c < 13; ++c) x[c] = plant[size_t(c) * B + b];
 #pragma unroll
   for (int c = 0; c < 4; ++c) u[c] = traj[row_index(0, 13 + c, 17, B, b)];
-  discrete_step(p, x, x + 3, x + 7, u);
+  gm::discrete_step_any(p, x, u);
   if (disturbance) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) x[7 + c] += disturbance[size_t(c) * B + b];
@@ -998,7 +1003,7 @@ k_rollout_constant(const __grid_constant__ DeviceParams p, const double *x0 /*[1
   for (int c = 0; c < 13; ++c) x[c] = x0[size_t(c) * B + b];
   for (int i = 0; i < N; ++i) {
     store_point(traj, i, B, b, x, u);
-    discrete_step(p, x, x + 3, x + 7, u);
+    gm::discrete_step_any(p, x, u);
   }
 }
 

@@ -71,7 +71,10 @@ class BatchILQR:
     """``ILQR<QuadrotorModel>`` over a batch, on one B200."""
 
     def __init__(self, mass_kg, inertia, arm_length_m, torque_to_thrust_ratio_m, g_mpss, Q, R, dt_s,
-                 options: ILQROptions | None = None, device: int = 0):
+                 options: ILQROptions | None = None, device: int = 0, model_flags: int = 0):
+        """``model_flags``: 0 = the reference's ``QuadrotorModel``; ``_capi.MODEL_RK4`` /
+        ``MODEL_CORIOLIS`` select a second dynamics function behind the ModelT concept
+        (``ilqr.hh:25-44``), ``MODEL_GENERIC`` the model-agnostic kernels for the reference model."""
         self._h = None
         self.options = options if options is not None else ILQROptions()
         self.dt_s = float(dt_s)
@@ -91,6 +94,9 @@ class BatchILQR:
         if rc != _capi.OK:
             raise QilqrError(rc)
         self._h = h
+        self.model_flags = int(model_flags)
+        if self.model_flags:
+            self._check(_capi.lib().qilqr_set_model_variant(self._h, C.c_int(self.model_flags)))
 
     # ---- lifetime -----------------------------------------------------------------
     def close(self):

@@ -22,18 +22,19 @@ def O():
     return oracle
 
 
-def make_solver(model=None, options=None, **overrides):
+def make_solver(model=None, options=None, model_flags=0, **overrides):
     """BatchILQR for a model dict (quadrotorilqr_b200.problems.default_model style)."""
     from quadrotorilqr_b200 import BatchILQR, problems
 
     m = dict(problems.default_model() if model is None else model)
     m.update(overrides)
     return BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"],
-                     m["g_mpss"], m["Q"], m["R"], m["dt_s"], options)
+                     m["g_mpss"], m["Q"], m["R"], m["dt_s"], options, model_flags=model_flags)
 
 
-def oracle_config(O, model, options):
+def oracle_config(O, model, options, model_kind=0):
     return O.make_config(
+        model_kind=model_kind,
         mass_kg=model["mass_kg"], inertia=model["inertia"], arm_length_m=model["arm_length_m"],
         torque_to_thrust_ratio_m=model["torque_to_thrust_ratio_m"], g_mpss=model["g_mpss"],
         Q=model["Q"], R=model["R"], dt_s=model["dt_s"],
