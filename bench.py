@@ -40,6 +40,10 @@ N_KNOTS = 40
 # dense as-written FLOPs per knot, counted by the oracle's FLOP-counting scalar
 # (oracle.count_flops on a converged hover trajectory)
 F_BWD, F_ROLL, F_COST = 30231.3, 721.2, 581.2
+# the same counts for the model variants of --model-variant (dense chain rule through the RK4 stages as
+# the oracle's QuadrotorModelVariant writes it); 4 = the reference model on the model-agnostic kernels
+VARIANT_FLOPS = {1: (72487.0, 2118.1, 585.0), 2: (30266.0, 745.2, 585.0), 3: (72559.0, 2190.1, 585.0),
+                 4: (F_BWD, F_ROLL, F_COST)}
 
 
 def env_int(name, default):
@@ -179,6 +183,9 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--model-variant", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="NOT the headline: 0 = the reference's QuadrotorModel (BASELINE config); 1 RK4, 2 Coriolis, "
+                         "3 both, 4 = reference model on the model-agnostic kernels (include/qilqr.h QILQR_MODEL_*)")
     ap.add_argument("--pipeline", type=int, default=8,
                     help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
     args = ap.parse_args()
@@ -214,7 +221,7 @@ def main():
 
     def make_solver():
         s_ = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
-                       m["Q"], m["R"], m["dt_s"], opts, device=local_rank)
+                       m["Q"], m["R"], m["dt_s"], opts, device=local_rank, model_flags=args.model_variant)
         return s_
 
     # P solver handles = a P-deep software pipeline of batches: each handle is driven by its own host
@@ -376,9 +383,10 @@ def main():
     # ---- roofline of the dominant kernel (backward pass), rank 0 -----------------------------------
     peak = ctypes.c_double(0.0)
     _capi.lib().qilqr_measure_fp64_peak(ctypes.c_int(local_rank), ctypes.byref(peak))
-    bwd_flops = bwd_knots * F_BWD
+    f_bwd, f_roll, f_cost = VARIANT_FLOPS.get(args.model_variant, (F_BWD, F_ROLL, F_COST))
+    bwd_flops = bwd_knots * f_bwd
     achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
-    roll_achieved = roll_knots * (F_ROLL + F_COST) / (roll_ms * 1e-3) / 1e12 if roll_ms > 0 else None
+    roll_achieved = roll_knots * (f_roll + f_cost) / (roll_ms * 1e-3) / 1e12 if roll_ms > 0 else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -389,6 +397,8 @@ def main():
     bwd_bytes = bwd_knots * (17 + 52) * 8.0
     traffic, traffic_note = None, None
     try:
+        if args.model_variant:
+            raise LookupError("no ncu traffic capture is wired in for the model variants")
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         n_bwd_launches = max(1, ser["solver_iterations"])
         traffic = tj["backward_dram_bytes_per_problem_knot"] * bwd_knots / n_bwd_launches
@@ -398,12 +408,14 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)",
+        "kernel": ("backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)"
+                   if not args.model_variant else
+                   "backward pass = k_linearise_dense + k_riccati_dense (model-agnostic ILQR::backwards_pass)"),
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": (achieved / peak.value) if (achieved and peak.value) else None,
         "peak_source": "measured in this run: register-resident DFMA kernel (qilqr_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
-        "flops_per_problem_knot": F_BWD,
+        "flops_per_problem_knot": f_bwd,
         "flops_definition": "dense as-written reference arithmetic counted by the oracle's FLOP-counting scalar",
         "traffic": traffic, "traffic_note": traffic_note,
         "share_of_step": bwd_ms / (serial_ms * n_serial),
@@ -424,6 +436,8 @@ def main():
                                f"(Philox seed {args.seed})",
                    "cache": "inputs larger than L2 (356 MB trajectories + 1.4 GB gains per step vs 126 MB L2)",
                    "parallelism": f"{world} independent shard(s), one process per GPU",
+                   **({"model_variant": f"{args.model_variant} (NOT the BASELINE model: see --model-variant)"}
+                      if args.model_variant else {}),
                    "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream each); "
                                "each step is one full batch"},
         "serial_ms_per_step": serial_ms,

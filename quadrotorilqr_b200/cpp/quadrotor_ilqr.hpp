@@ -107,9 +107,11 @@ inline qilqr_options_t to_c(const ILQROptions &o) {
 // RAII handle on a solver of the CUDA library.
 struct Handle {
   qilqr_solver_t *h = nullptr;
-  Handle(const qilqr_model_t &m, const Mat12 &Q, const Mat4 &R, double dt_s, const ILQROptions &o, int device = 0) {
+  Handle(const qilqr_model_t &m, const Mat12 &Q, const Mat4 &R, double dt_s, const ILQROptions &o, int device = 0,
+         int model_flags = 0) {
     const qilqr_options_t co = to_c(o);
     check(qilqr_create(&m, Q.data(), R.data(), dt_s, &co, device, &h));
+    if (model_flags) check(qilqr_set_model_variant(h, model_flags));
   }
   ~Handle() { qilqr_destroy(h); }
   Handle(const Handle &) = delete;
@@ -153,6 +155,7 @@ struct QuadrotorModel {
   double arm_length_m_;
   double torque_to_thrust_ratio_m_;
   double g_mpss_;
+  int model_flags_ = 0;  // QILQR_MODEL_*: 0 = the reference's model (see QuadrotorModelVariant below)
 
   QuadrotorModel(double mass_kg, const Mat3 &inertia, double arm_length_m, double torque_to_thrust_ratio_m,
                  double g_mpss = 9.81)
@@ -207,12 +210,25 @@ struct QuadrotorModel {
   qilqr_solver_t *handle(double dt_s) const {
     auto it = handles_.find(dt_s);
     if (it == handles_.end())
-      it = handles_.emplace(dt_s, std::make_shared<Handle>(c_model(), Identity12(), Identity4(), dt_s, ILQROptions{})).first;
+      it = handles_.emplace(dt_s, std::make_shared<Handle>(c_model(), Identity12(), Identity4(), dt_s, ILQROptions{}, 0,
+                                                           model_flags_)).first;
     return it->second->h;
   }
 
  private:
   mutable std::map<double, std::shared_ptr<Handle>> handles_;
+};
+
+// A second model behind the ModelT concept of ilqr.hh:25-44 (not in the reference): the same state
+// manifold with an RK4 integrator (the scheme commented out at quadrotor_model.cc:51-63) and/or the
+// Coriolis term -omega x v.  ILQR<QuadrotorModelVariant> runs on the model-agnostic CUDA kernels.
+struct QuadrotorModelVariant : QuadrotorModel {
+  QuadrotorModelVariant(double mass_kg, const Mat3 &inertia, double arm_length_m, double torque_to_thrust_ratio_m,
+                        double g_mpss, bool rk4, bool coriolis)
+      : QuadrotorModel(mass_kg, inertia, arm_length_m, torque_to_thrust_ratio_m, g_mpss) {
+    model_flags_ = (rk4 ? QILQR_MODEL_RK4 : 0) | (coriolis ? QILQR_MODEL_CORIOLIS : 0);
+    if (!model_flags_) model_flags_ = QILQR_MODEL_GENERIC;  // the reference dynamics on the generic kernels
+  }
 };
 
 namespace detail {
@@ -360,7 +376,8 @@ struct ILQR {  // ilqr.hh:25-206
 
   ILQR(ModelT model, CostFunc cost_function, double dt_s, ILQROptions options)
       : model_(std::move(model)), cost_function_(std::move(cost_function)), dt_s_(dt_s), options_(options),
-        h_(std::make_shared<Handle>(model_.c_model(), cost_function_.Q(), cost_function_.R(), dt_s, options)),
+        h_(std::make_shared<Handle>(model_.c_model(), cost_function_.Q(), cost_function_.R(), dt_s, options, 0,
+                                    model_.model_flags_)),
         desired_(flatten<ModelT>(cost_function_.desired_trajectory())) {}
 
   // ilqr.hh:53-87

@@ -125,6 +125,31 @@ static void SolveFindsOptimalTrajectory() {  // ilqr_test.cc:179-190
   for (const auto &s : sols) check_approx_traj_eq(f.current_traj_, s, 1e-6);
   EXPECT_EQ(res[0].backward_passes, res[2].backward_passes);
 }
+// ILQR<ModelT> with a second ModelT: the fixture's problem (ilqr_test.cc:68-100, :179-190)
+// solved with the RK4 variant and with the reference dynamics on the model-agnostic kernels.
+static void SecondModelSolveFindsOptimalTrajectory() {
+  using VSolver = ILQR<QuadrotorModelVariant>;
+  using VCost = CostFunction<QuadrotorModelVariant>;
+  for (int variant = 0; variant < 3; ++variant) {
+    const bool rk4 = variant >= 1, coriolis = variant == 2;
+    Trajectory<QuadrotorModelVariant> identity;
+    for (const auto &pt : create_identity_traj(3, 0.1)) identity.push_back({pt.time_s, pt.state, pt.control});
+    VSolver ilqr{QuadrotorModelVariant{mass_kg, Identity3(), 1.0, 1.0, 0.0, rk4, coriolis},
+                 VCost{Identity12(), Identity4(), identity}, 0.1,
+                 ILQROptions{LineSearchParams{0.5, 0.5, 10}, ConvergenceCriteria{1e-12, 1e-12, 100}}};
+    VSolver::ControlUpdate u{};
+    u.ff_update = {100, 1, 100, 1};
+    const VSolver::ControlUpdateTrajectory upd(3, u);
+    const auto initial = ilqr.forward_sim(identity, upd);
+    EXPECT_TRUE(ilqr.cost_trajectory(initial) > 1.0);
+    const auto [opt, debug] = ilqr.solve(initial);
+    for (size_t i = 0; i < opt.size(); ++i) {
+      const auto d = (opt[i].state - identity[i].state).coeffs();
+      for (int j = 0; j < 12; ++j) EXPECT_NEAR(d[j], 0.0, 1e-6);
+      for (int j = 0; j < 4; ++j) EXPECT_NEAR(opt[i].control[j], 0.0, 1e-6);
+    }
+  }
+}
 static void DiscreteDynamicsKnownAnswers() {  // quadrotor_model_test.cc:94-143
   QuadrotorModel quad{mass_kg, Identity3(), 1.0, 1.0};
   State x = create_identity_state();
@@ -188,6 +213,7 @@ int main() {
        BackwardsPassExpectedValueReductionIsNegativeIfReductionPossible},
       {"ILQRFixture.LineSearchFindsStepSizeThatReducesCost", LineSearchFindsStepSizeThatReducesCost},
       {"ILQRFixture.SolveFindsOptimalTrajectory", SolveFindsOptimalTrajectory},
+      {"SecondModel.SolveFindsOptimalTrajectory", SecondModelSolveFindsOptimalTrajectory},
       {"QuadrotorModelTest.DiscreteDynamicsKnownAnswers", DiscreteDynamicsKnownAnswers},
       {"StateTangentAndExceptions", StateTangentAndExceptions},
       {"ComputeCost.ReturnsZeroCostWhenZeroError", CostZeroAtZeroError},
