@@ -357,12 +357,19 @@ def main():
     vec = torch.tensor([dev_ms, t_wall * 1e3, float(converged), float(prob_iters), float(ls_failed),
                         float(max_iter_hit), float(launches), e2e["t"] if e2e else 0.0,
                         float(e2e["converged"]) if e2e else 0.0], dtype=torch.float64, device=dev)
+    gathered_converged = None
     if dist is not None:
         mx = vec.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vec.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
+        # the path's one collective: per-problem result records of every shard (24 B/problem) over NCCL
+        from quadrotorilqr_b200 import sharding
+
+        allres = sharding.gather_results(dist, res_dev[0].view(B, 24))
+        st_all = np.frombuffer(allres.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)["status"]
+        gathered_converged = int(np.sum((st_all == 1) | (st_all == 2)))
     else:
         mx = sm = vec.cpu().numpy()
     if rank != 0:
@@ -449,6 +456,9 @@ def main():
         "solver_iterations_per_step": solver_iters / args.steps,
         "device_event_ms_per_step": step_ms, "wall_ms_per_step": wall_ms,
         "gpu_launches": int(sm[6] / world),
+        **({"gathered_results": {"problems": B * world, "converged": gathered_converged,
+                                 "note": "ncclAllGather of the per-problem result records after the timed region"}}
+           if gathered_converged is not None else {}),
         "clocks": clocks,
         "roofline": roofline,
     }

@@ -50,6 +50,12 @@ def _worker(rank, world, port, out_dir):
     vec = torch.from_numpy(sharding.summarize_results(res))
     mx, sm = sharding.reduce_stats(dist, vec)
     np.save(os.path.join(out_dir, f"traj{rank}.npy"), r["traj"])
+    allres = sharding.gather_results(dist, res)  # per-problem records of every rank, in rank order
+    soa = torch.from_numpy(np.ascontiguousarray(r["traj"][:, :, 1:].transpose(1, 2, 0)))  # [N, 17, B]
+    alltraj = sharding.gather_trajectories(dist, soa)
+    if rank == 1:
+        np.save(os.path.join(out_dir, "gathered_res.npy"), allres)
+        np.save(os.path.join(out_dir, "gathered_traj.npy"), alltraj.numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "sum.npy"), sm.numpy())
         np.save(os.path.join(out_dir, "max.npy"), mx.numpy())
@@ -68,6 +74,11 @@ def test_two_rank_shards_match_unsharded(tmp_path):
     conv = np.sum((full["status"] == 1) | (full["status"] == 2))
     assert sm[0] == conv and sm[1] == full["backward_passes"].sum() and sm[5] == world * B_PER_RANK
     assert sm[4] == full["rollouts"].sum()
+    # the gather of per-problem results and (on request) trajectories, as seen by rank 1
+    g = np.load(tmp_path / "gathered_res.npy")
+    assert np.array_equal(g["status"], full["status"]) and np.array_equal(g["backward_passes"], full["backward_passes"])
+    gt = np.load(tmp_path / "gathered_traj.npy")  # [N, 17, world * B]
+    assert np.array_equal(gt.transpose(2, 0, 1), full["traj"][:, :, 1:])
 
 
 def test_strong_shard_partition():
