@@ -14,6 +14,7 @@
 #include <string>
 #include <thread>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "qilqr_api_kernels.cuh"
@@ -72,6 +73,8 @@ struct qilqr_solver {
   int g4_kpp = 4;                // knots linearised per phase by the quad kernel (1, 2 or 4)
   bool force_t1 = false;         // QILQR_BACKWARD=t1: the one-thread-per-problem kernel (cross-checks)
   bool split_backward = true;    // linearise kernel + TMA-fed Riccati kernel (default) vs the fused quad kernel
+  bool rollout_ws = true;        // role-specialised rollout kernel (3 warps per 32 problems); QILQR_ROLLOUT=thread: one thread per problem
+  int ws_threshold = 4096;       // ... used for launches of at most this many problems (latency-bound); QILQR_WS_THRESHOLD
   bool generic_path = false;     // model-agnostic kernels (dense J_x, J_u): any model variant, or forced for cross-checks
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
@@ -250,13 +253,12 @@ int wait_counts(qilqr_solver *S, cudaStream_t st) {
 template <int KPP>
 void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
   const size_t smem = sizeof(double) * g4::smem_doubles(KPP);
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag configured;  // several solver handles may launch from different host threads
+  std::call_once(configured, [&] {
     cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
+  });
   k_backward_g4<KPP><<<blocks_for(ba.n, 8), 32, smem, S->cur>>>(S->p, ba);
 }
 // ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
@@ -268,12 +270,11 @@ int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
   static const size_t extra = std::getenv("QILQR_RICCATI_EXTRA_SMEM") ? std::atoi(std::getenv("QILQR_RICCATI_EXTRA_SMEM")) : 0;
   const size_t smem = sizeof(double) * g4::split_smem_doubles(DENSEQ) + extra;  // `extra`: occupancy experiments only
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag configured;
+  std::call_once(configured, [&] {
     cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
+  });
   const size_t threads = size_t(n8) * ba.pr.N;
   k_linearise<DENSEQ><<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   k_riccati_g4<DENSEQ><<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
@@ -286,12 +287,11 @@ int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
   const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * dn::DREC;
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
   const size_t smem = sizeof(double) * dn::smem_doubles();
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag configured;
+  std::call_once(configured, [&] {
     cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
+  });
   const size_t threads = size_t(n8) * ba.pr.N;
   k_linearise_dense<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   k_riccati_dense<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
@@ -301,6 +301,8 @@ int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
 // forward_sim (+ cost, + line-search bookkeeping) with the dynamics of the configured model
 void launch_rollout(qilqr_solver *S, const RolloutArgs &ra, int threads, cudaStream_t st) {
   if (S->generic_path) k_rollout<true><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
+  // (with parallel step sizes every evaluation, wide or not, stays on the one-thread-per-problem kernel)
+  else if (S->rollout_ws && S->opt.num_parallel_alphas <= 1 && threads <= S->ws_threshold) k_rollout_ws<<<blocks_for(threads, 32), 96, 0, st>>>(S->p, ra);
   else k_rollout<false><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
 }
 int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
@@ -565,6 +567,8 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
     if (std::string(e) == "split") S->split_backward = true;
     if (std::string(e) == "fused") S->split_backward = false;
   }
+  if (const char *e = std::getenv("QILQR_ROLLOUT")) S->rollout_ws = std::string(e) != "thread";
+  if (const char *e = std::getenv("QILQR_WS_THRESHOLD")) S->ws_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4) S->g4_kpp = v;

@@ -109,15 +109,18 @@ QD void m3_hat_mul(const double *t, const double *M, double *C) {
   }
 }
 
-// Eigen toRotationMatrix (what manif's rotation() returns)
+// Eigen toRotationMatrix (what manif's rotation() returns).  Every product and sum is rounded on its own
+// (no FMA contraction), as in the reference build: besides matching it more closely, this keeps the
+// entries independent of which of them a caller uses (a kernel that needs only the third row would
+// otherwise get differently-contracted code after dead-code elimination).
 QD void quat_to_rot(const double *q, double *R) {
   const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
-  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
-  const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
-  const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
-  R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
-  R[3] = txy + twz;         R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.0 - (txx + tyy);
+  const double twx = __dmul_rn(tx, q[3]), twy = __dmul_rn(ty, q[3]), twz = __dmul_rn(tz, q[3]);
+  const double txx = __dmul_rn(tx, q[0]), txy = __dmul_rn(ty, q[0]), txz = __dmul_rn(tz, q[0]);
+  const double tyy = __dmul_rn(ty, q[1]), tyz = __dmul_rn(tz, q[1]), tzz = __dmul_rn(tz, q[2]);
+  R[0] = __dsub_rn(1.0, __dadd_rn(tyy, tzz)); R[1] = __dsub_rn(txy, twz);               R[2] = __dadd_rn(txz, twy);
+  R[3] = __dadd_rn(txy, twz);               R[4] = __dsub_rn(1.0, __dadd_rn(txx, tzz)); R[5] = __dsub_rn(tyz, twx);
+  R[6] = __dsub_rn(txz, twy);               R[7] = __dadd_rn(tyz, twx);               R[8] = __dsub_rn(1.0, __dadd_rn(txx, tyy));
 }
 // manif SO3::compose: Hamilton product + first-order renormalisation
 // The products are rounded individually (no FMA contraction) so that conj(q) (x) q has an
@@ -445,8 +448,8 @@ QD void state_minus(const double *x /*13*/, const double *xd /*13*/, double *dx 
 #pragma unroll
   for (int i = 0; i < 6; ++i) dx[6 + i] = x[7 + i] - xd[7 + i];
 }
-// cost = dx^T Q dx + du^T R du, evaluated as (dx^T Q) dx
-QD double quadratic_cost(const DeviceParams &p, const double *dx, const double *du) {
+// cost = dx^T Q dx + du^T R du, evaluated as (dx^T Q) dx   (cost.hh:47-48)
+QD double quadratic_cost_state(const DeviceParams &p, const double *dx) {
   double cx = 0.0;
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
@@ -455,6 +458,9 @@ QD double quadratic_cost(const DeviceParams &p, const double *dx, const double *
     for (int i = 1; i < 12; ++i) y = fma(dx[i], p.Q[12 * i + j], y);
     cx = (j == 0) ? y * dx[0] : fma(y, dx[j], cx);
   }
+  return cx;
+}
+QD double quadratic_cost_control(const DeviceParams &p, const double *du) {
   double cu = 0.0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -463,7 +469,10 @@ QD double quadratic_cost(const DeviceParams &p, const double *dx, const double *
     for (int i = 1; i < 4; ++i) y = fma(du[i], p.R[4 * i + j], y);
     cu = (j == 0) ? y * du[0] : fma(y, du[j], cu);
   }
-  return cx + cu;
+  return cu;
+}
+QD double quadratic_cost(const DeviceParams &p, const double *dx, const double *du) {
+  return quadratic_cost_state(p, dx) + quadratic_cost_control(p, du);
 }
 
 }  // namespace qilqr

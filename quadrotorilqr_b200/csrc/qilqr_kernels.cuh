@@ -128,6 +128,46 @@ struct RolloutArgs {
   int palpha;        // MODE_WIDE: step sizes evaluated per problem
 };
 
+// line_search() / solve() bookkeeping after one candidate rollout of problem b (ilqr.hh:70-84, 182-193)
+QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, double alpha, double cost) {
+  const int B = a.pr.B;
+  const SolveState &st = a.st;
+  st.rollouts[b] += 1;
+  st.new_cost[b] = cost;
+  const double cur_cost = st.cost[b];
+  bool accept;
+  if (a.mode == MODE_SOLVE && a.iter == 0) {
+    accept = true;  // ilqr.hh:70-73: no acceptance test on the first iteration
+  } else {
+    const double desired = p.desired_reduction_frac * (alpha * st.qutk[b] + alpha * alpha * st.ktquuk[b] / 2.0);
+    accept = (cost - cur_cost < desired);  // ilqr.hh:186; NaN -> reject
+  }
+  if (accept) {
+    st.sel[b] ^= 1;
+    st.cost[b] = cost;
+    st.accepted_iter[b] = a.iter;
+    const int nd = st.ndebug[b];
+    if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
+    st.ndebug[b] = nd + 1;
+    if (a.mode == MODE_SOLVE && a.iter > 0 && is_converged(p, cur_cost, cost)) {
+      st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
+      st.phase[b] = PHASE_DONE;
+    } else if (a.mode == MODE_LINE_SEARCH) {
+      st.phase[b] = PHASE_DONE;
+    } else {
+      st.phase[b] = PHASE_ACTIVE;
+    }
+  } else {
+    st.alpha[b] = alpha * p.step_update;  // ilqr.hh:189
+    const int ls = st.ls_iter[b] + 1;
+    st.ls_iter[b] = ls;
+    if (ls >= p.ls_max_iters) {
+      st.status[b] = isfinite(cost) ? QILQR_STATUS_LINE_SEARCH_FAILED : QILQR_STATUS_NONFINITE;  // ilqr.hh:191-193
+      st.phase[b] = PHASE_DONE;
+    }
+  }
+}
+
 #ifndef QILQR_ROLLOUT_MINB
 #define QILQR_ROLLOUT_MINB 2
 #endif
@@ -206,42 +246,150 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
     a.cost_out[size_t(wide_j) * B + b] = cost;
     return;
   }
-  // ---- line_search / solve bookkeeping ----
-  const SolveState &st = a.st;
-  st.rollouts[b] += 1;
-  st.new_cost[b] = cost;
-  const double cur_cost = st.cost[b];
-  bool accept;
-  if (a.mode == MODE_SOLVE && a.iter == 0) {
-    accept = true;  // ilqr.hh:70-73: no acceptance test on the first iteration
+  rollout_finish(p, a, b, alpha, cost);
+}
+
+// ---------------------------------------------------------------------------
+// The same rollout with THREE ROLE-SPECIALISED WARPS per 32 problems (reference model only).
+// Within one knot the reference's chain  x (-) xbar -> u -> acceleration  does not feed the pose update
+// (explicit Euler: pose+ = pose o Exp(dt v) needs only x), and the cost needs only (x, u):
+//   warp A "control": delta = x (-) xbar, u = ubar + alpha k + K delta | acceleration, v+ = v + dt a
+//   warp B "pose":    pose+ = pose o Exp(dt v)                         |
+//   warp C "cost":    dx = x (-) x_d, dx^T Q dx, store the state       | du^T R du, running cost, store u
+// with two CTA barriers per knot (x_i ready | u_i ready) and 6 kB of shared memory for the hand-over.
+// The critical path per knot drops from the sum of the three chains to the longest one plus the
+// acceleration; every value is computed by the same instruction sequence as in k_rollout, so the two
+// kernels agree bit for bit (tests/test_gpu_parity.py::test_rollout_kernels_agree).
+// ---------------------------------------------------------------------------
+#ifndef QILQR_WS_MINB
+#define QILQR_WS_MINB 2
+#endif
+__global__ void __launch_bounds__(96, QILQR_WS_MINB) k_rollout_ws(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
+  __shared__ double s_pose[2][7][32], s_vel[6][32], s_u[4][32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * 32 + lane;
+  const bool valid = t0 < a.n;
+  const int t = valid ? t0 : a.n - 1;  // idle lanes shadow the last problem (they must reach the barriers) and write nothing
+  const int b = a.list ? a.list[t] : t;
+  const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
+  const int bd = (Bd == 1) ? 0 : b;
+  const double *cur;
+  double *cand;
+  double alpha;
+  if (a.mode == MODE_FORWARD) {
+    cur = a.cur; cand = a.out; alpha = a.alpha_in[b];
   } else {
-    const double desired = p.desired_reduction_frac * (alpha * st.qutk[b] + alpha * alpha * st.ktquuk[b] / 2.0);
-    accept = (cost - cur_cost < desired);  // ilqr.hh:186; NaN -> reject
+    const int s = a.st.sel[b];
+    cur = s ? a.pr.buf1 : a.pr.buf0;
+    cand = s ? a.pr.buf0 : a.pr.buf1;
+    alpha = a.st.alpha[b];
   }
-  if (accept) {
-    st.sel[b] ^= 1;
-    st.cost[b] = cost;
-    st.accepted_iter[b] = a.iter;
-    const int nd = st.ndebug[b];
-    if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
-    st.ndebug[b] = nd + 1;
-    if (a.mode == MODE_SOLVE && a.iter > 0 && is_converged(p, cur_cost, cost)) {
-      st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
-      st.phase[b] = PHASE_DONE;
-    } else if (a.mode == MODE_LINE_SEARCH) {
-      st.phase[b] = PHASE_DONE;
+  const bool want_cost = (a.mode != MODE_FORWARD) || (a.cost_out != nullptr);
+
+  double x[13], ubar[4];
+  load_point(cur, 0, B, b, x, ubar);  // state = current_traj.front().state (ilqr.hh:156)
+  if (role == 1) {
+#pragma unroll
+    for (int c = 0; c < 7; ++c) s_pose[0][c][lane] = x[c];
+  } else if (role == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s_vel[c][lane] = x[7 + c];
+  }
+  double cost = 0.0, cx = 0.0;
+  for (int i = 0; i < N; ++i) {
+    __syncthreads();  // x_i = (s_pose[i & 1], s_vel) is complete
+    if (role == 0) {
+      double xbar[13], gk[4], gK[48];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) xbar[c] = ldg_early(&cur[row_index(i, c, 17, B, b)]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ubar[c] = ldg_early(&cur[row_index(i, 13 + c, 17, B, b)]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gk[e] = ldg_early(&a.pr.gk[row_index(i, e, 4, B, b)]);
+#pragma unroll
+      for (int e = 0; e < 48; ++e) gK[e] = ldg_early(&a.pr.gK[row_index(i, e, 48, B, b)]);
+#pragma unroll
+      for (int c = 0; c < 7; ++c) x[c] = s_pose[i & 1][c][lane];
+      double d[12];
+      state_minus(x, xbar, d, nullptr);  // (state - current_traj[i].state).coeffs()
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double Kd = gK[12 * j] * d[0];
+#pragma unroll
+        for (int s = 1; s < 12; ++s) Kd = fma(gK[12 * j + s], d[s], Kd);
+        ubar[j] = (ubar[j] + alpha * gk[j]) + Kd;  // from here on: the new control u_i
+        s_u[j][lane] = ubar[j];
+      }
+    } else if (role == 1) {
+      // pose part of discrete_step: pose+ = pose o Exp(dt * body velocity)
+      double vel[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) vel[c] = s_vel[c][lane];
+      double R[9];
+      quat_to_rot(x + 3, R);
+      const double dv[3] = {p.dt * vel[0], p.dt * vel[1], p.dt * vel[2]};
+      const double dw[3] = {p.dt * vel[3], p.dt * vel[4], p.dt * vel[5]};
+      double Jl[9], te[3], qe[4], Rt[3], qn[4];
+      so3_ljac(dw, Jl);
+      m3_vec(Jl, dv, te);
+      so3_exp(dw, qe);
+      m3_vec(R, te, Rt);
+      quat_compose(x + 3, qe, qn);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = Rt[c] + x[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x[3 + c] = qn[c];
+#pragma unroll
+      for (int c = 0; c < 7; ++c) s_pose[(i + 1) & 1][c][lane] = x[c];
     } else {
-      st.phase[b] = PHASE_ACTIVE;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) x[c] = s_pose[i & 1][c][lane];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) x[7 + c] = s_vel[c][lane];
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 13; ++c) cand[row_index(i, c, 17, B, b)] = x[c];
+      }
+      if (want_cost) {
+        double xd[13], dx[12];
+#pragma unroll
+        for (int c = 0; c < 13; ++c) xd[c] = a.pr.desired[row_index(i, c, 17, Bd, bd)];
+        state_minus(x, xd, dx, nullptr);
+        cx = quadratic_cost_state(p, dx);
+      }
     }
-  } else {
-    st.alpha[b] = alpha * p.step_update;  // ilqr.hh:189
-    const int ls = st.ls_iter[b] + 1;
-    st.ls_iter[b] = ls;
-    if (ls >= p.ls_max_iters) {
-      st.status[b] = isfinite(cost) ? QILQR_STATUS_LINE_SEARCH_FAILED : QILQR_STATUS_NONFINITE;  // ilqr.hh:191-193
-      st.phase[b] = PHASE_DONE;
+    __syncthreads();  // u_i is in s_u; every reader of v_i is done
+    if (role == 0) {
+      // velocity part of discrete_step: v+ = v + dt * body_acceleration(x_i, u_i)
+      double R[9], acc[6];
+      quat_to_rot(x + 3, R);
+      body_acceleration(p, R, x + 7, ubar, acc);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        x[7 + c] = x[7 + c] + p.dt * acc[c];
+        s_vel[c][lane] = x[7 + c];
+      }
+    } else if (role == 2) {
+      double u[4], du[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = s_u[j][lane];
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cand[row_index(i, 13 + c, 17, B, b)] = u[c];
+      }
+      if (want_cost) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) du[j] = u[j] - a.pr.desired[row_index(i, 13 + j, 17, Bd, bd)];
+        cost = cost + (cx + quadratic_cost_control(p, du));
+      }
     }
   }
+  if (role != 2 || !valid) return;
+  if (a.mode == MODE_FORWARD) {
+    if (a.cost_out) a.cost_out[b] = cost;
+    return;
+  }
+  rollout_finish(p, a, b, alpha, cost);
 }
 
 // ---------------------------------------------------------------------------

@@ -470,3 +470,36 @@ def test_quad_and_thread_backward_kernels_agree(monkeypatch):
         monkeypatch.delenv("QILQR_KPP")
         k2, K2, a2, c2 = s_k.backwards_pass(initial, desired)
         assert np.array_equal(K2, Kq) and np.array_equal(k2, kq)  # same arithmetic, different staging
+
+
+def test_rollout_kernels_agree(monkeypatch):
+    """The role-specialised rollout (three warps per 32 problems: control / pose / cost) runs the same
+    instruction sequences as the one-thread-per-problem rollout: bit-identical trajectories, costs and solves."""
+    from quadrotorilqr_b200 import problems
+
+    model, opts = problems.hover_model(), problems.default_options(False)
+    s_ws = make_solver(model, opts)
+    monkeypatch.setenv("QILQR_ROLLOUT", "thread")
+    s_th = make_solver(model, opts)
+    monkeypatch.delenv("QILQR_ROLLOUT")
+    for B in (1, 37, 200):  # ragged: partial warps and partial CTAs
+        desired, initial = hover_batch(s_ws, B, 40, seed=3)
+        k, K, _, _ = s_ws.backwards_pass(initial, desired)
+        for alpha in (1.0, 0.25):
+            fa, fb = s_ws.forward_sim(initial, k, K, alpha), s_th.forward_sim(initial, k, K, alpha)
+            assert np.array_equal(fa, fb), f"max abs diff {np.abs(fa - fb).max():.3e}"
+        a, b = s_ws.solve(initial, desired, want_gains=True, hist_cap=100), s_th.solve(initial, desired, want_gains=True,
+                                                                                      hist_cap=100)
+        assert np.array_equal(a["results"], b["results"])
+        assert np.array_equal(a["traj"], b["traj"]) and np.array_equal(a["K"], b["K"])
+        assert np.array_equal(a["cost_history"], b["cost_history"])
+    # the reference's default problem through line_search() as well
+    m2, o2 = problems.default_model(), problems.default_options(False)
+    d2 = problems.default_desired_trajectory()
+    s2 = make_solver(m2, o2)
+    monkeypatch.setenv("QILQR_ROLLOUT", "thread")
+    s3 = make_solver(m2, o2)
+    monkeypatch.delenv("QILQR_ROLLOUT")
+    r2, r3 = s2.solve(d2[None], d2, hist_cap=100), s3.solve(d2[None], d2, hist_cap=100)
+    assert np.array_equal(r2["results"], r3["results"]) and np.array_equal(r2["traj"], r3["traj"])
+    assert np.array_equal(r2["cost_history"], r3["cost_history"])
