@@ -11,12 +11,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quadrotorilqr_b200 import BatchILQR, problems  # noqa: E402
 
 
-def run(opts, B, N, env=None):
+def run(opts, B, N, env=None, model_flags=0):
     for k, v in (env or {}).items():
         os.environ[k] = v
     m = problems.hover_model()
     s = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"], m["Q"],
-                  m["R"], m["dt_s"], opts)
+                  m["R"], m["dt_s"], opts, model_flags=model_flags)
     for k in (env or {}):
         del os.environ[k]
     d = problems.hover_desired_trajectory(N)
@@ -34,3 +34,7 @@ if __name__ == "__main__":
     print(run(base, 13, 6, {"QILQR_BACKWARD": "fused"})["backward_passes"])           # fused quad kernel
     print(run(dataclasses.replace(base, num_parallel_alphas=3, symmetrize_vxx=True, populate_debug=True), 10, 7)["rollouts"])
     print(run(base, 5, 5, {"QILQR_BACKWARD": "t1"})["backward_passes"])               # thread-per-problem kernel
+    print(run(base, 40, 7, {"QILQR_ROLLOUT": "thread"})["rollouts"])                  # thread-per-problem rollout only
+    print(run(base, 70, 7)["rollouts"])                                               # role-specialised rollout (3 CTAs, ragged)
+    print(run(dataclasses.replace(base, symmetrize_vxx=True), 11, 6, model_flags=3)["backward_passes"])  # dense kernels, RK4 + Coriolis
+    print(run(base, 9, 5, model_flags=4)["backward_passes"])                          # dense kernels, reference model
