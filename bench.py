@@ -474,7 +474,9 @@ def main():
         O.build()
         cfg = oracle_config(O, m, opts)
         cores = O.hardware_threads()
-        sample = int(min(B, max(64, args.cpu_sample_per_core * cores)))
+        # one pass of ~10-15 s of wall time (the whole batch on a 16-core box); the reference arm's steps use a
+        # quarter of that so that its W + K steps end within a few minutes
+        sample = int(min(B, max(64, 4 * args.cpu_sample_per_core * cores)))
         init_cpu = cpu_initial_trajectories(O, cfg, problems, m, desired, x0[:sample])
         dt, conv, its = run_cpu_sample(O, cfg, desired, init_cpu, cores)
         line["cpu_baseline"] = {
