@@ -21,6 +21,7 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <ostream>
 #include <stdexcept>
 #include <tuple>
 #include <string>
@@ -92,6 +93,8 @@ inline bool operator==(const LineSearchParams &a, const LineSearchParams &b) {
 inline bool operator==(const ConvergenceCriteria &a, const ConvergenceCriteria &b) {
   return a.rtol == b.rtol && a.atol == b.atol && a.max_iters == b.max_iters;
 }
+// (the reference's version ends in `lhs.populate_debug && rhs.populate_debug`, ilqr_options.cc:17-21, which
+// makes two option sets with populate_debug == false unequal; that slip is not reproduced)
 inline bool operator==(const ILQROptions &a, const ILQROptions &b) {
   return a.line_search_params == b.line_search_params && a.convergence_criteria == b.convergence_criteria &&
          a.populate_debug == b.populate_debug && a.symmetrize_vxx == b.symmetrize_vxx &&
@@ -283,6 +286,65 @@ struct ILQRIterDebug {  // ilqr_debug.hh:9-13
 };
 template <class ModelT>
 using ILQRDebug = std::vector<ILQRIterDebug<ModelT>>;
+
+// Equality and printing, as the reference defines them (quadrotor_model.cc:252-263, trajectory.hh:16-44,
+// ilqr_debug.hh:15-19).  manif compares group elements and tangents approximately (tolerance
+// Constants<double>::eps = 1e-14); here: coefficient-wise within 1e-14 (relative to max(1, |value|)), a
+// unit quaternion and its negative being the same rotation.
+namespace detail {
+inline bool approx(double a, double b) { return std::fabs(a - b) <= 1e-14 * std::fmax(1.0, std::fmax(std::fabs(a), std::fabs(b))); }
+template <size_t N>
+bool approx(const std::array<double, N> &a, const std::array<double, N> &b, double sign = 1.0) {
+  for (size_t i = 0; i < N; ++i)
+    if (!approx(a[i], sign * b[i])) return false;
+  return true;
+}
+template <size_t N>
+void print(std::ostream &out, const std::array<double, N> &v) {
+  for (size_t i = 0; i < N; ++i) out << (i ? " " : "") << v[i];
+}
+}  // namespace detail
+inline bool operator==(const SE3 &a, const SE3 &b) {
+  return detail::approx(a.translation, b.translation) &&
+         (detail::approx(a.quaternion, b.quaternion) || detail::approx(a.quaternion, b.quaternion, -1.0));
+}
+inline bool operator==(const QuadrotorModel::State &lhs, const QuadrotorModel::State &rhs) {
+  return detail::approx(lhs.body_velocity, rhs.body_velocity) && lhs.inertial_from_body == rhs.inertial_from_body;
+}
+inline bool operator!=(const QuadrotorModel::State &lhs, const QuadrotorModel::State &rhs) { return !(lhs == rhs); }
+inline std::ostream &operator<<(std::ostream &out, const QuadrotorModel::State &state) {
+  out << "inertial_from_body: ";
+  detail::print(out, state.inertial_from_body.translation);
+  out << " ";
+  detail::print(out, state.inertial_from_body.quaternion);
+  out << ", body velocity: ";
+  detail::print(out, state.body_velocity);
+  return out;
+}
+template <class ModelT>
+bool operator==(const TrajectoryPoint<ModelT> &lhs, const TrajectoryPoint<ModelT> &rhs) {
+  return lhs.time_s == rhs.time_s && lhs.control == rhs.control && lhs.state == rhs.state;
+}
+template <class ModelT>
+bool operator!=(const TrajectoryPoint<ModelT> &lhs, const TrajectoryPoint<ModelT> &rhs) { return !(lhs == rhs); }
+template <class ModelT>
+std::ostream &operator<<(std::ostream &out, const TrajectoryPoint<ModelT> &pt) {
+  out << "{\n\ttime_s: " << pt.time_s << ",\n\tstate: " << pt.state << ",\n\tcontrol:";
+  detail::print(out, pt.control);
+  return out << "\n}";
+}
+template <class ModelT>
+std::ostream &operator<<(std::ostream &out, const Trajectory<ModelT> &traj) {
+  out << "{\n";
+  for (const auto &pt : traj) out << pt << ",\n";
+  return out << "}";
+}
+template <class ModelT>
+bool operator==(const ILQRIterDebug<ModelT> &lhs, const ILQRIterDebug<ModelT> &rhs) {
+  return lhs.trajectory == rhs.trajectory && lhs.cost == rhs.cost;
+}
+template <class ModelT>
+bool operator!=(const ILQRIterDebug<ModelT> &lhs, const ILQRIterDebug<ModelT> &rhs) { return !(lhs == rhs); }
 
 template <class ModelT>
 std::vector<double> flatten(const Trajectory<ModelT> &t) {

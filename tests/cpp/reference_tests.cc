@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <functional>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -204,6 +205,39 @@ static void CostZeroAtZeroError() {  // cost_test.cc:27-39
   EXPECT_EQ(diffs.xu[7], 0.0);
 }
 
+// trajectory_test.cc:20-48, ilqr_debug_test.cc, ilqr_options_test.cc: the equality operators (host only)
+static void EqualityOperators() {
+  const TrajectoryPoint<QuadrotorModel> pt0{0.0, create_identity_state(), Control{0, 0, 0, 0}};
+  EXPECT_TRUE(pt0 == pt0);
+  auto pt1 = pt0;
+  pt1.time_s = 1.0;
+  EXPECT_TRUE(pt0 != pt1);
+  pt1 = pt0;
+  QuadrotorModel::StateTangent off{};
+  off.body_velocity[2] = 1.0;
+  pt1.state = pt1.state + off;
+  EXPECT_TRUE(pt0 != pt1);
+  pt1 = pt0;
+  pt1.control = {1, 1, 1, 1};
+  EXPECT_TRUE(pt0 != pt1);
+  auto pt2 = pt0;  // q and -q are the same rotation
+  for (auto &c : pt2.state.inertial_from_body.quaternion) c = -c;
+  EXPECT_TRUE(pt0 == pt2);
+  const ILQRIterDebug<QuadrotorModel> d0{{pt0}, 23.3};
+  auto d1 = d0;
+  EXPECT_TRUE(d0 == d1);
+  d1.cost = 5;
+  EXPECT_TRUE(d0 != d1);
+  d1 = d0;
+  d1.trajectory.front().time_s = 1.0;
+  EXPECT_TRUE(d0 != d1);
+  EXPECT_TRUE((LineSearchParams{1.0, 2.0, 3} == LineSearchParams{1.0, 2.0, 3}));
+  EXPECT_TRUE(!(LineSearchParams{0.0, 2.0, 3} == LineSearchParams{1.0, 2.0, 3}));
+  std::ostringstream os;
+  os << Trajectory<QuadrotorModel>{pt0};
+  EXPECT_TRUE(os.str().find("time_s: 0") != std::string::npos && os.str().find("body velocity") != std::string::npos);
+}
+
 int main() {
   const std::vector<std::pair<std::string, std::function<void()>>> tests = {
       {"ILQRFixture.ForwardSimGeneratesCorrectTrajectory", ForwardSimGeneratesCorrectTrajectory},
@@ -216,6 +250,7 @@ int main() {
       {"SecondModel.SolveFindsOptimalTrajectory", SecondModelSolveFindsOptimalTrajectory},
       {"QuadrotorModelTest.DiscreteDynamicsKnownAnswers", DiscreteDynamicsKnownAnswers},
       {"StateTangentAndExceptions", StateTangentAndExceptions},
+      {"EqualityOperators", EqualityOperators},
       {"ComputeCost.ReturnsZeroCostWhenZeroError", CostZeroAtZeroError},
   };
   for (const auto &t : tests) {

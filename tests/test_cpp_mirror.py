@@ -32,4 +32,4 @@ def test_reference_gtests_pass_through_the_cpp_mirror():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("[  OK  ]") == 10
+    assert out.stdout.count("[  OK  ]") == 11
