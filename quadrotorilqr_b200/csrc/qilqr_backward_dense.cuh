@@ -6,13 +6,13 @@
 //
 //   k_linearise_dense  one thread per (problem, knot): discrete_dynamics with differentials of
 //                      the configured model variant (qilqr_model_generic.cuh) + CostFunction
-//                      differentials (cost.hh:47-57), written as 352-double records in tiles
+//                      differentials (cost.hh:47-57), written as 316-double records in tiles
 //                      rec[tile of 8 problems][knot][element][8]
 //   k_riccati_dense    one warp per tile, 4 lanes per problem; lane c owns the 12x3 column
 //                      block c of V_xx, Q_xx and of the gains in registers.  Record tiles
-//                      (22.5 kB) arrive by TMA bulk copies, double-buffered; the products
-//                      whose operands live on other lanes go through a 253-double exchange
-//                      area per problem in shared memory:
+//                      (20 kB) arrive by TMA bulk copies, double-buffered; the products
+//                      whose operands live on other lanes go through a 193-double exchange
+//                      area per problem in shared memory (52.8 kB per warp: 4 warps per SM):
 //        step 1  lane c:  M[:,c] = J_x^T V[:,c],  (J_u^T V)[:,c],  Q_x[c],  Q_u   -> smem
 //        step 2  lane c:  Q_xx[:,c] = C_xx[:,c] + M J_x[:,c];  Q_xu[c,:] = M[c,:] J_u;
 //                         Q_uu = C_uu + (J_u^T V) J_u   (replicated)
@@ -29,16 +29,19 @@
 
 namespace qilqr {
 namespace dn {
-constexpr int D_A = 0, D_B = 144, D_CX = 192, D_CU = 204, D_CXX = 208, DREC = 352;
-constexpr int TILE = DREC * 8;  // doubles per (tile of 8 problems, knot): 22528 B
-constexpr int E_M = 0, E_BTV = 144, E_KTQ = 192, E_VX = 240, DXS = 253;  // exchange area per problem; stride odd
-__host__ __device__ constexpr int smem_doubles() { return 2 * TILE + 8 * DXS + 2; }
-struct DenseLayout {  // cost differentials inside a dense record (see g4::G4Layout); C.xx row-major 12x12
+// record: J_x (144), J_u (48), C.x (12), C.u (4), and the pose/pose, pose/velocity, velocity/pose 6x6 blocks
+// of C.xx (the velocity/velocity block is the constant 2 Q_vv and stays out of the record)
+constexpr int D_A = 0, D_B = 144, D_CX = 192, D_CU = 204, D_CPP = 208, D_CPV = 244, D_CVP = 280, DREC = 316;
+constexpr int TILE = DREC * 8;  // doubles per (tile of 8 problems, knot): 20224 B
+// exchange area per problem: M (144) and J_u^T V (48); (K^T Q_uu) and v_x reuse the start of M. Stride odd.
+constexpr int E_M = 0, E_BTV = 144, E_KTQ = 0, E_VX = 48, DXS = 193;
+__host__ __device__ constexpr int smem_doubles() { return 2 * TILE + 8 * DXS + 36 + 2; }
+struct DenseLayout {  // cost differentials inside a dense record (see g4::G4Layout)
   __host__ __device__ static constexpr int cx(int j) { return D_CX + j; }
   __host__ __device__ static constexpr int cu(int j) { return D_CU + j; }
-  __host__ __device__ static constexpr int cpp(int i, int j) { return D_CXX + 12 * i + j; }
-  __host__ __device__ static constexpr int cpv(int i, int j) { return D_CXX + 12 * i + 6 + j; }
-  __host__ __device__ static constexpr int cvp(int i, int j) { return D_CXX + 12 * (6 + i) + j; }
+  __host__ __device__ static constexpr int cpp(int i, int j) { return D_CPP + 6 * i + j; }
+  __host__ __device__ static constexpr int cpv(int i, int j) { return D_CPV + 6 * i + j; }
+  __host__ __device__ static constexpr int cvp(int i, int j) { return D_CVP + 6 * i + j; }
 };
 }  // namespace dn
 
@@ -64,10 +67,6 @@ __global__ void __launch_bounds__(128) k_linearise_dense(const __grid_constant__
     gm::discrete_with_jacobians(p, x, u, xn, dst + D_A * 8, dst + D_B * 8, 8);
   }
   g4::cost_to_record<8, true, DenseLayout>(p, x, u, xd, ud, dst);
-#pragma unroll
-  for (int r = 6; r < 12; ++r)
-#pragma unroll
-    for (int c = 6; c < 12; ++c) dst[(D_CXX + 12 * r + c) * 8] = 2.0 * p.Q[12 * r + c];  // C.xx velocity block = 2 Q_vv
 }
 
 __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ DeviceParams p,
@@ -84,7 +83,9 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
   const int B = a.pr.B, N = a.pr.N;
   double *bufs = smem;
   double *xch = smem + 2 * TILE + q * DXS;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + 2 * TILE + 8 * DXS);
+  double *s2Qvv = smem + 2 * TILE + 8 * DXS;  // C.xx velocity block = 2 Q_vv (cost.hh:52 with J = blkdiag(.., I))
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36);
+  for (int e = lane; e < 36; e += 32) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -181,6 +182,9 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
     __syncwarp();
 
     // ---- step 2: Q_xx[:,c], Q_xu rows of c, Q_uu ----
+    const double *ctop = rec + ((c < 2) ? D_CPP + 3 * c : D_CPV + 3 * (c - 2)) * 8;
+    const double *cbot = (c < 2) ? rec + (D_CVP + 3 * c) * 8 : s2Qvv + 3 * (c - 2);
+    const int cbot_rs = (c < 2) ? 48 : 6, cbot_cs = (c < 2) ? 8 : 1;
     double Qxxc[36];
 #pragma unroll
     for (int r = 0; r < 12; ++r) {
@@ -194,8 +198,10 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
         const double mv = xch[E_M + 12 * r + k];
         s0 = fma(mv, Ac[3 * k], s0); s1 = fma(mv, Ac[3 * k + 1], s1); s2 = fma(mv, Ac[3 * k + 2], s2);
       }
-      const double *cxx = rec + (D_CXX + 12 * r + 3 * c) * 8;
-      Qxxc[3 * r] = cxx[0] + s0; Qxxc[3 * r + 1] = cxx[8] + s1; Qxxc[3 * r + 2] = cxx[16] + s2;
+      // C.xx[r][3c + j]: rows 0..5 from the pp | pv blocks of the record, rows 6..11 from the vp block | 2 Q_vv table
+      const double *cxx = (r < 6) ? ctop + 48 * r : cbot + cbot_rs * (r - 6);
+      const int cs = (r < 6) ? 8 : cbot_cs;
+      Qxxc[3 * r] = cxx[0] + s0; Qxxc[3 * r + 1] = cxx[cs] + s1; Qxxc[3 * r + 2] = cxx[2 * cs] + s2;
     }
     double Qxuc[12], Quu[16];  // Qxuc[4 i + j] = Q_xu[3 c + i][j]
     {
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
 #pragma unroll
         for (int i2 = 0; i2 < 3; ++i2) a.pr.gK[row_index(i, 12 * j + 3 * c + i2, 48, B, b)] = Kc[3 * j + i2];
     }
+    __syncwarp();  // every lane has finished reading M (step 2): its first 60 doubles are reused for K^T Q_uu and v_x
     double KtQc[12];  // (K^T Q_uu)[3 c + i][l]
 #pragma unroll
     for (int i2 = 0; i2 < 3; ++i2)
@@ -305,7 +312,8 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
     }
 #pragma unroll
     for (int e = 0; e < 12; ++e) vx[e] = xch[E_VX + e];
-    if (p.symmetrize_vxx) {  // V <- (V + V^T) / 2 through the (now free) M area
+    if (p.symmetrize_vxx) {  // V <- (V + V^T) / 2 through the M area
+      __syncwarp();  // ... once every lane has read K^T Q_uu and v_x, which live at its start
 #pragma unroll
       for (int r = 0; r < 12; ++r)
 #pragma unroll

@@ -217,14 +217,40 @@ QD void cont_strip(const DeviceParams &p, const ContBlocks &F, int s, double *D)
 // State recursion of discrete_dynamics for any variant, keeping the Jacobian blocks of every stage:
 //   Fs[i]: continuous Jacobian at stage i (Euler: only Fs[0]);  Es[0..2]: Euler-step Jacobians of RK4
 //   stages 1..3;  Es[3]: Jacobians of the final step x (+) dt xdot.
+struct ContStore {  // ContBlocks without the redundancy of the three skew matrices (kept per stage in local memory)
+  double gz[3], Wc[9], w[3], v[3];
+};
+QD void compact(const ContBlocks &F, ContStore &C) {
+  C.gz[0] = F.G[7]; C.gz[1] = F.G[2]; C.gz[2] = F.G[3];
+  C.w[0] = F.nW[5]; C.w[1] = F.nW[6]; C.w[2] = F.nW[1];
+  C.v[0] = F.V[7];  C.v[1] = F.V[2];  C.v[2] = F.V[3];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) C.Wc[e] = F.Wc[e];
+}
+QD void expand(const ContStore &C, ContBlocks &F) {
+  const double *gz = C.gz, *w = C.w, *v = C.v;
+  F.G[0] = 0.0;    F.G[1] = -gz[2]; F.G[2] = gz[1];
+  F.G[3] = gz[2];  F.G[4] = 0.0;    F.G[5] = -gz[0];
+  F.G[6] = -gz[1]; F.G[7] = gz[0];  F.G[8] = 0.0;
+  F.nW[0] = 0.0;   F.nW[1] = w[2];  F.nW[2] = -w[1];
+  F.nW[3] = -w[2]; F.nW[4] = 0.0;   F.nW[5] = w[0];
+  F.nW[6] = w[1];  F.nW[7] = -w[0]; F.nW[8] = 0.0;
+  F.V[0] = 0.0;   F.V[1] = -v[2]; F.V[2] = v[1];
+  F.V[3] = v[2];  F.V[4] = 0.0;   F.V[5] = -v[0];
+  F.V[6] = -v[1]; F.V[7] = v[0];  F.V[8] = 0.0;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) F.Wc[e] = C.Wc[e];
+}
 struct StageBlocks {
-  ContBlocks Fs[4];
+  ContStore Fs[4];
   EulerBlocks Es[4];
 };
 QD void discrete_stages(const DeviceParams &p, const double *x, const double *u, double *xn, StageBlocks &W) {
   double k[12];
   if (!p.integrator) {  // quadrotor_model.cc:33-49
-    continuous_with_blocks(p, x, u, k, W.Fs[0]);
+    ContBlocks F;
+    continuous_with_blocks(p, x, u, k, F);
+    compact(F, W.Fs[0]);
     euler_with_blocks(x, k, p.dt, xn, W.Es[3]);
     return;
   }
@@ -240,7 +266,9 @@ QD void discrete_stages(const DeviceParams &p, const double *x, const double *u,
     // stage 0: x (+) 0 equals x up to the quaternion renormalisation of compose; its J_lhs = I, J_rhs = 0
     if (i == 0) euler_state(x, k, 0.0, xi);
     else euler_with_blocks(x, k, dti, xi, W.Es[i - 1]);
-    continuous_with_blocks(p, xi, u, k, W.Fs[i]);
+    ContBlocks F;
+    continuous_with_blocks(p, xi, u, k, F);
+    compact(F, W.Fs[i]);
 #pragma unroll
     for (int e = 0; e < 12; ++e) xdot[e] = xdot[e] + ci * k[e];
   }
@@ -253,7 +281,9 @@ QD void discrete_stages(const DeviceParams &p, const double *x, const double *u,
 template <int n>
 QD void jacobian_strip(const DeviceParams &p, const StageBlocks &W, int s, double *out, int ld, int stride) {
   double D[12 * n], T[12 * n];
-  cont_strip<n>(p, W.Fs[0], s, D);
+  ContBlocks F;
+  expand(W.Fs[0], F);
+  cont_strip<n>(p, F, s, D);
   if (!p.integrator) {
     euler_rhs_mul<n>(W.Es[3], D, T);
   } else {
@@ -266,7 +296,8 @@ QD void jacobian_strip(const DeviceParams &p, const StageBlocks &W, int s, doubl
       const double ci = (i == 3) ? 1.0 / 6.0 : 2.0 / 6.0;
       euler_rhs_mul<n>(W.Es[i - 1], D, T);
       if (n == 3) euler_lhs_add_strip(W.Es[i - 1], s, T);
-      cont_mul<n>(p, W.Fs[i], T, D);
+      expand(W.Fs[i], F);
+      cont_mul<n>(p, F, T, D);
       if (n == 4) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) D[32 + e] = D[32 + e] + p.JuC[e];
