@@ -16,7 +16,7 @@ m, opts = problems.hover_model(), problems.default_options(False)
 s = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"], m["Q"], m["R"],
               m["dt_s"], opts)
 d = problems.hover_desired_trajectory(N)
-x0 = problems.hover_initial_states(B, seed=2026)
+x0 = problems.hover_initial_states(B, seed=int(os.environ.get("SEED", 2026)))
 init = s.forward_sim(problems.constant_state_trajectory(x0, N, m["dt_s"], d[0, 14:18]), np.zeros((B, N, 4)),
                      np.zeros((B, N, 48)))
 r = s.solve(init, d, hist_cap=100)
@@ -31,7 +31,7 @@ err = np.max(np.abs(r["traj"] - o["traj"]), axis=(1, 2)) / scale
 cerr = np.abs(res["final_cost"] - o["final_cost"]) / np.maximum(1.0, np.abs(o["final_cost"]))
 diff = np.where(~same)[0]
 out = {
-    "batch": B, "identical_decisions": int(same.sum()), "different_decisions": int(diff.size),
+    "batch": B, "seed": int(os.environ.get("SEED", 2026)), "identical_decisions": int(same.sum()), "different_decisions": int(diff.size),
     "max_rel_traj_err_where_identical": float(err[same].max()), "max_rel_cost_err_where_identical": float(cerr[same].max()),
     "max_rel_traj_err_where_different": float(err[diff].max()) if diff.size else 0.0,
     "max_rel_cost_err_where_different": float(cerr[diff].max()) if diff.size else 0.0,
