@@ -218,7 +218,9 @@ void launch_compact(qilqr_solver *S, const int *list, int n, const int *phase, i
                     int phase_s = PHASE_SEARCH, int phase_a = PHASE_ACTIVE) {
   const int seq = ++S->seq;
   if (n <= 4096) {
-    k_compact<<<1, 1024, 0, S->cur>>>(list, n, phase, out_s, out_a, S->d_counts, phase_s, phase_a, seq);
+    // a small CTA is enough for the short lists of a solve's tail (and fits next to the bulk kernels' CTAs)
+    const int threads = n <= 512 ? 128 : 1024;
+    k_compact<<<1, threads, 0, S->cur>>>(list, n, phase, out_s, out_a, S->d_counts, phase_s, phase_a, seq);
     ++S->launches;
     return;
   }

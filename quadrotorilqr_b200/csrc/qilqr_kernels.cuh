@@ -855,10 +855,10 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
                                                  int phase_a = PHASE_ACTIVE, int seq = 0) {
   __shared__ int warp_s[32], warp_a[32];
   __shared__ int base_s, base_a;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;  // any multiple of 32 threads
   if (tid == 0) { base_s = 0; base_a = 0; }
   __syncthreads();
-  for (int start = 0; start < n_in; start += 1024) {
+  for (int start = 0; start < n_in; start += blockDim.x) {
     const int idx = start + tid;
     int b = -1, ph = -1;
     if (idx < n_in) {
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
     if (lane == 0) { warp_s[wid] = __popc(ms); warp_a[wid] = __popc(ma); }
     __syncthreads();
     if (wid == 0) {
-      int vs = warp_s[lane], va = warp_a[lane];
+      int vs = lane < nw ? warp_s[lane] : 0, va = lane < nw ? warp_a[lane] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int ts = __shfl_up_sync(0xffffffffu, vs, o), ta = __shfl_up_sync(0xffffffffu, va, o);
