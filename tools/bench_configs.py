@@ -2,6 +2,8 @@
 """Timings of the other BASELINE.json configs (the driver's headline is bench.py = config 3):
   c1  the reference's default problem, batch 1 (latency)
   c2  batch 1024 random hover problems
+  c3w batch 65536 WAYPOINT problems: every problem tracks its own 4-segment piecewise-constant position
+      path (desired_count = batch), one batch at a time (bench.py measures the hover variant, pipelined)
   c4  N = 1000 figure-eight tracking, batch 4096, 8 parallel alphas, symmetrised V_xx
   c5  receding-horizon MPC, 16384 quadrotors x 500 closed-loop steps, warm-started re-solves
 Prints one JSON line per config; run under gpurun and keep the output under profiles/."""
@@ -58,7 +60,7 @@ def time_solves(s, init, des, reps, warm=1):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c1,c2,c4,c5")
+    ap.add_argument("--configs", default="c1,c2,c3w,c4,c5")
     ap.add_argument("--mpc-steps", type=int, default=500)
     ap.add_argument("--mpc-batch", type=int, default=16384)
     args = ap.parse_args()
@@ -89,6 +91,27 @@ def main():
                           "solves_per_s": conv / dt, "converged": conv, "iterations_per_solve":
                           float(res["backward_passes"].mean()), "max_iterations": int(res["backward_passes"].max())}),
               flush=True)
+    if "c3w" in todo:
+        m, o = problems.hover_model(), problems.default_options(False)
+        s = mk(m, o)
+        N, B = 40, 65536
+        base = problems.hover_desired_trajectory(N)
+        way = np.random.Generator(np.random.Philox(key=3)).uniform(-1, 1, (B, 4, 3))  # waypoints U[-1,1]^3
+        desired = np.repeat(base[None], B, axis=0)
+        for seg in range(4):
+            desired[:, seg * N // 4:(seg + 1) * N // 4, 1:4] = way[:, seg][:, None, :]
+        _, init, _ = device_problem(s, problems.hover_initial_states(B, seed=2026), base, N, dev)
+        des = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
+        s.pack_trajectory_device(torch.from_numpy(desired).to(dev), des)
+        torch.cuda.synchronize()
+        dt, res = time_solves(s, init, des, 3)
+        conv = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
+        print(json.dumps({"config": "c3w batch 65536 waypoint problems (per-problem desired trajectories), N=40, "
+                                    "device-resident, one batch at a time", "ms_per_batch": 1e3 * dt,
+                          "solves_per_s": conv / dt, "converged": conv, "converged_fraction": conv / B,
+                          "iterations_per_solve": float(res["backward_passes"].mean()),
+                          "max_iters_hit": int(np.sum(res["status"] == 3)),
+                          "line_search_failures": int(np.sum(res["status"] >= 4))}), flush=True)
     if "c4" in todo:
         N, dt_s, B = 1000, 0.02, 4096
         m = dict(problems.hover_model(), dt_s=dt_s)
