@@ -99,7 +99,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "sm_min_mhz": min(sm) if sm else None, "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
 def oracle_config(O, m, opts):
