@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--model-variant", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="NOT the headline: 0 = the reference's QuadrotorModel (BASELINE config); 1 RK4, 2 Coriolis, "
                          "3 both, 4 = reference model on the model-agnostic kernels (include/qilqr.h QILQR_MODEL_*)")
+    ap.add_argument("--stagger-ms", type=float, default=-1.0,
+                    help="start offset between pipelined handles (default: one measured step time; 0 = start together)")
     ap.add_argument("--pipeline", type=int, default=8,
                     help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
     args = ap.parse_args()
@@ -246,7 +248,7 @@ def main():
     torch.cuda.synchronize()
 
     STAT_KEYS = ("backward_ms", "rollout_ms", "backward_problem_knots", "rollout_problem_knots",
-                 "problem_iterations", "problem_rollouts", "solver_iterations")
+                 "problem_iterations", "problem_rollouts", "solver_iterations", "bulk_wall_ms", "tail_wall_ms")
 
     def device_step(j, acc=None):
         with torch.cuda.stream(streams[j]):
@@ -257,12 +259,19 @@ def main():
             for k_ in STAT_KEYS:
                 acc[k_] += st[k_]
 
-    def run_pipelined(step_fn, nsteps):
-        """Issue `nsteps` steps round-robin over the P handles, one host thread per handle."""
+    def run_pipelined(step_fn, nsteps, stagger_s=0.0):
+        """Issue `nsteps` steps round-robin over the P handles, one host thread per handle.
+
+        `stagger_s`: handle j starts j * stagger_s late.  Handles that start together stay in lock step (they
+        share the GPU equally, so their throughput-bound phases end together) and then sit in their
+        latency-bound tails together with the GPU almost idle; started one step apart, one handle's tail
+        always overlaps another's bulk."""
         accs = [{k_: 0 for k_ in STAT_KEYS} for _ in range(P)]
         counts = [nsteps // P + (1 if j < nsteps % P else 0) for j in range(P)]
 
         def worker(j):
+            if stagger_s > 0 and j > 0 and counts[j] > 0:
+                time.sleep(j * stagger_s)
             for _ in range(counts[j]):
                 step_fn(j, accs[j])
 
@@ -282,8 +291,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- `value`: device-resident ----------------------------------------------------------
-    run_pipelined(device_step, max(args.warmup, P))
+    n_warm = max(args.warmup, P)
+    run_pipelined(device_step, n_warm)  # first calls: allocation of the workspaces
     barrier()
+    t_w0 = time.perf_counter()
+    run_pipelined(device_step, n_warm)
+    barrier()
+    # start offset between handles inside the timed regions: one step time (measured on the warm-up), unless given
+    stagger_s = (args.stagger_ms * 1e-3 if args.stagger_ms >= 0 else (time.perf_counter() - t_w0) / n_warm) if P > 1 else 0.0
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sum(s_.kernel_launch_count for s_ in solvers)
@@ -293,7 +308,7 @@ def main():
     for j in range(P):
         ev0[j].record(streams[j])
     t_wall0 = time.perf_counter()
-    tot = run_pipelined(device_step, args.steps)
+    tot = run_pipelined(device_step, args.steps, stagger_s)
     for j in range(P):
         ev1[j].record(streams[j])
     barrier()
@@ -345,7 +360,7 @@ def main():
         run_pipelined(host_step, P)
         barrier()
         t0 = time.perf_counter()
-        run_pipelined(host_step, e2e_steps)
+        run_pipelined(host_step, e2e_steps, stagger_s)
         barrier()
         e2e_t = time.perf_counter() - t0
         r2 = np.frombuffer(res_host[0].numpy().tobytes(), dtype=RESULT_DTYPE)
@@ -445,8 +460,8 @@ def main():
                    "parallelism": f"{world} independent shard(s), one process per GPU",
                    **({"model_variant": f"{args.model_variant} (NOT the BASELINE model: see --model-variant)"}
                       if args.model_variant else {}),
-                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream each); "
-                               "each step is one full batch"},
+                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream each), "
+                               f"started {1e3 * stagger_s:.1f} ms apart; each step is one full batch"},
         "serial_ms_per_step": serial_ms,
         "serial_value": (converged / (serial_ms * 1e-3)) if serial_ms else None,
         "us_per_iteration": us_per_iter,
@@ -454,6 +469,8 @@ def main():
         "line_search_failures": int(sm[4]), "max_iters_hit": int(sm[5]),
         "iterations_per_solve": total_iters / args.steps / (B * world),
         "solver_iterations_per_step": solver_iters / args.steps,
+        # host wall time a batch spends in its throughput-bound bulk and in its latency-bound tail (rank 0, pipelined)
+        "bulk_wall_ms_per_batch": tot["bulk_wall_ms"] / args.steps, "tail_wall_ms_per_batch": tot["tail_wall_ms"] / args.steps,
         "device_event_ms_per_step": step_ms, "wall_ms_per_step": wall_ms,
         "gpu_launches": int(sm[6] / world),
         **({"gathered_results": {"problems": B * world, "converged": gathered_converged,

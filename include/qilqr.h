@@ -237,6 +237,8 @@ typedef struct {
   double rollout_ms;           /* CUDA-event time spent in rollout/line-search kernels */
   int64_t backward_problem_knots; /* problem-knots processed by backward kernels */
   int64_t rollout_problem_knots;  /* problem-knots processed by rollout kernels */
+  double bulk_wall_ms;            /* host wall time of the solve loop while more than hi_threshold problems were active */
+  double tail_wall_ms;            /* ... and after the switch to the high-priority tail stream */
 } qilqr_solve_stats_t;
 int qilqr_last_solve_stats(const qilqr_solver_t *solver, qilqr_solve_stats_t *out);
 /* Enable/disable per-kernel CUDA-event timing (adds a few microseconds per launch). */

@@ -75,6 +75,8 @@ class SolveStats(C.Structure):
         ("rollout_ms", C.c_double),
         ("backward_problem_knots", C.c_int64),
         ("rollout_problem_knots", C.c_int64),
+        ("bulk_wall_ms", C.c_double),
+        ("tail_wall_ms", C.c_double),
     ]
 
 

@@ -14,6 +14,7 @@
 #include <string>
 #include <thread>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -82,6 +83,9 @@ struct qilqr_solver {
   // workspace
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
       hist_d, debug_d, misc, wide_d, rec_d;
+  // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
+  DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map;
+  bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
   int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
   int *d_counts = nullptr;
 };
@@ -190,9 +194,11 @@ void llt_solve(const double *L, const double *b, double *x) {
 struct StateLayout {  // carve SolveState out of two flat buffers
   static constexpr int kDoubles = 5, kInts = 8;
 };
+SolveState make_state_from(double *d, int *i, int B, double *hist, int hist_cap);
 SolveState make_state(qilqr_solver *S, int B, double *hist, int hist_cap) {
-  double *d = S->state_d.as<double>();
-  int *i = S->state_i.as<int>();
+  return make_state_from(S->state_d.as<double>(), S->state_i.as<int>(), B, hist, hist_cap);
+}
+SolveState make_state_from(double *d, int *i, int B, double *hist, int hist_cap) {
   SolveState st;
   st.cost = d; st.new_cost = d + B; st.qutk = d + 2 * size_t(B); st.ktquuk = d + 3 * size_t(B); st.alpha = d + 4 * size_t(B);
   st.ls_iter = i; st.status = i + B; st.bwd = i + 2 * size_t(B); st.rollouts = i + 3 * size_t(B);
@@ -355,6 +361,8 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
 
   S->stats = qilqr_solve_stats_t{};
   const int64_t launches0 = S->launches;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto t_switch = t_begin;
 
   k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B);
   k_cost_trajectory<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, d_traj, d_desired, B, N, Bd, st.cost);
@@ -365,6 +373,10 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   const int *active = nullptr;  // nullptr = identity list
   int cur = 0;
   bool on_hi = false;
+  bool compacted = false;  // the remaining problems live in the dense mini-batch (pr / st point there)
+  const Problem pr_big = pr;
+  const SolveState st_big = st;
+  int B_eff = B, m_tail = 0;
   const int P_alpha = S->opt.num_parallel_alphas > 1 ? S->opt.num_parallel_alphas : 1;
   int *listF = S->lists.as<int>() + 4 * size_t(B);
   if (P_alpha > 1) QCUDA(S, S->wide_d.ensure(sizeof(double) * size_t(P_alpha) * B));
@@ -377,6 +389,35 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       st_ = S->stream_hi;
       S->cur = st_;
       on_hi = true;
+      t_switch = std::chrono::steady_clock::now();
+      if (S->tail_compaction && !capture_debug && active) {
+        // ... and into a dense mini-batch: m problems, pitch m instead of B
+        const int m = n_active;
+        const size_t md = size_t(m);
+        QCUDA(S, S->tail_traj.ensure(sizeof(double) * 2 * N * 17 * md));
+        QCUDA(S, S->tail_gains.ensure(sizeof(double) * N * 52 * md));
+        QCUDA(S, S->tail_sd.ensure(sizeof(double) * StateLayout::kDoubles * md));
+        QCUDA(S, S->tail_si.ensure(sizeof(int) * StateLayout::kInts * md));
+        QCUDA(S, S->tail_map.ensure(sizeof(int) * md));
+        if (Bd != 1) QCUDA(S, S->tail_des.ensure(sizeof(double) * N * 17 * md));
+        if (st.cost_hist) QCUDA(S, S->tail_hist.ensure(sizeof(double) * size_t(st.hist_cap) * md));
+        QCUDA(S, cudaMemcpyAsync(S->tail_map.ptr, active, sizeof(int) * md, cudaMemcpyDeviceToDevice, st_));
+        double *tt = S->tail_traj.as<double>(), *tg = S->tail_gains.as<double>();
+        double *mini_des = (Bd != 1) ? S->tail_des.as<double>() : nullptr;
+        Problem pm{m, N, Bd != 1 ? m : 1, tt, tt + size_t(N) * 17 * md, mini_des ? mini_des : d_desired, tg,
+                   tg + size_t(N) * 4 * md};
+        SolveState sm = make_state_from(S->tail_sd.as<double>(), S->tail_si.as<int>(), m,
+                                        st.cost_hist ? S->tail_hist.as<double>() : nullptr, st.hist_cap);
+        dim3 grid(blocks_for(m, 128), 32);
+        k_tail_gather<<<grid, 128, 0, st_>>>(pr_big, st_big, pm, sm, mini_des, S->tail_map.as<int>(), m);
+        ++S->launches;
+        pr = pm;
+        st = sm;
+        active = nullptr;  // identity list over the mini-batch
+        B_eff = m;
+        m_tail = m;
+        compacted = true;
+      }
     }
     const bool wide = P_alpha > 1 && i > 0;  // iteration 0 is an unconditional full step (ilqr.hh:70-73)
     BackwardArgs ba{pr, st, active, n_active, i, wide ? PHASE_WIDE : PHASE_SEARCH, 1, nullptr, nullptr};
@@ -436,7 +477,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
           launch_rollout(S, rw, n_wide * P_alpha, st_);
         }
         S->stats.rollout_problem_knots += int64_t(n_wide) * P_alpha * N;
-        k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B, S->wide_d.as<double>(), P_alpha);
+        k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B_eff, S->wide_d.as<double>(), P_alpha);
         launch_compact(S, listS[s], n_wide, st.phase, listS[1 - s], listF, PHASE_WIDE, PHASE_SEARCH);
         S->launches += 2;
         if ((rc = wait_counts(S, st_))) return rc;
@@ -455,10 +496,15 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     active = listA[cur];
     n_active = n_next;
   }
-  k_finalize<<<blocks_for(B, 256), 256, 0, st_>>>(st, B, d_results);
+  if (compacted) {
+    dim3 grid(blocks_for(m_tail, 128), 32);
+    k_tail_scatter<<<grid, 128, 0, st_>>>(pr_big, st_big, pr, st, S->tail_map.as<int>(), m_tail);
+    ++S->launches;
+  }
+  k_finalize<<<blocks_for(B, 256), 256, 0, st_>>>(st_big, B, d_results);
   {
     dim3 grid(blocks_for(B, 128), 64);
-    k_collect<<<grid, 128, 0, st_>>>(pr, st.sel);
+    k_collect<<<grid, 128, 0, st_>>>(pr_big, st_big.sel);
   }
   S->launches += 2;
   if (on_hi) {  // rejoin the solver's main stream
@@ -469,6 +515,12 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   QCUDA(S, cudaStreamSynchronize(S->stream));
   QCUDA(S, cudaGetLastError());
   S->stats.kernel_launches = S->launches - launches0;
+  {
+    const auto t_end = std::chrono::steady_clock::now();
+    if (!on_hi) t_switch = t_end;
+    S->stats.bulk_wall_ms = std::chrono::duration<double, std::milli>(t_switch - t_begin).count();
+    S->stats.tail_wall_ms = std::chrono::duration<double, std::milli>(t_end - t_switch).count();
+  }
   return QILQR_OK;
 }
 
@@ -570,6 +622,7 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
     if (std::string(e) == "fused") S->split_backward = false;
   }
   if (const char *e = std::getenv("QILQR_ROLLOUT")) S->rollout_ws = std::string(e) != "thread";
+  if (const char *e = std::getenv("QILQR_TAIL_COMPACTION")) S->tail_compaction = std::atoi(e) != 0;
   if (const char *e = std::getenv("QILQR_WS_THRESHOLD")) S->ws_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);
@@ -600,7 +653,8 @@ void qilqr_destroy(qilqr_solver_t *S) {
   cudaStreamSynchronize(S->stream);
   for (DeviceBuffer *b : {&S->buf1, &S->gk, &S->gK, &S->state_d, &S->state_i, &S->lists, &S->desired_soa,
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
-                          &S->debug_d, &S->misc, &S->wide_d, &S->rec_d})
+                          &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->tail_traj, &S->tail_gains, &S->tail_des,
+                          &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
@@ -703,6 +757,8 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
     total_stats.rollout_ms += S->stats.rollout_ms;
     total_stats.backward_problem_knots += S->stats.backward_problem_knots;
     total_stats.rollout_problem_knots += S->stats.rollout_problem_knots;
+    total_stats.bulk_wall_ms += S->stats.bulk_wall_ms;
+    total_stats.tail_wall_ms += S->stats.tail_wall_ms;
     double *u_log = d_control_log ? d_control_log + size_t(t) * 4 * B : nullptr;
     k_mpc_advance<<<blocks_for(B, 128), 128, 0, S->stream>>>(S->p, d_traj, d_plant, d_dist, u_log, B, N);
     ++S->launches;

@@ -1008,6 +1008,49 @@ __global__ void k_collect(Problem pr, const int *sel) {
   const int rows = pr.N * 17;
   for (int r = blockIdx.y; r < rows; r += gridDim.y) pr.buf0[size_t(r) * pr.B + b] = pr.buf1[size_t(r) * pr.B + b];
 }
+// Tail compaction.  Once only a few problems of a large batch are still iterating, their data sits 8*B bytes
+// apart in every row of the SoA arrays (one 32-byte sector and, across rows, one page-table entry per value).
+// k_tail_gather moves the m remaining problems (map[t], ordered) into a dense mini-batch of pitch m -- current
+// trajectory, per-problem desired trajectory if any, solver state, cost history -- the remaining iterations run
+// there with unchanged kernels, and k_tail_scatter puts trajectory, last gains, state and history back.
+// Same arithmetic on the same values: results are bit-identical with and without the compaction.
+__global__ void k_tail_gather(Problem big, SolveState sb, Problem mini, SolveState sm, double *mini_desired,
+                              const int *map, int m) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int b = map[t], B = big.B;
+  const double *src = sb.sel[b] ? big.buf1 : big.buf0;
+  const int rows = big.N * 17;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    mini.buf0[size_t(r) * m + t] = src[size_t(r) * B + b];
+    if (mini_desired) mini_desired[size_t(r) * m + t] = big.desired[size_t(r) * B + b];
+  }
+  for (int r = blockIdx.y; r < sb.hist_cap; r += gridDim.y)
+    if (sb.cost_hist) sm.cost_hist[size_t(r) * m + t] = sb.cost_hist[size_t(r) * B + b];
+  if (blockIdx.y != 0) return;
+  sm.cost[t] = sb.cost[b]; sm.new_cost[t] = sb.new_cost[b]; sm.qutk[t] = sb.qutk[b]; sm.ktquuk[t] = sb.ktquuk[b];
+  sm.alpha[t] = sb.alpha[b];
+  sm.ls_iter[t] = sb.ls_iter[b]; sm.status[t] = sb.status[b]; sm.bwd[t] = sb.bwd[b]; sm.rollouts[t] = sb.rollouts[b];
+  sm.ndebug[t] = sb.ndebug[b]; sm.phase[t] = sb.phase[b]; sm.accepted_iter[t] = sb.accepted_iter[b];
+  sm.sel[t] = 0;  // the gathered trajectory is the mini-batch's buffer 0
+}
+__global__ void k_tail_scatter(Problem big, SolveState sb, Problem mini, SolveState sm, const int *map, int m) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int b = map[t], B = big.B, N = big.N;
+  double *dst = sb.sel[b] ? big.buf1 : big.buf0;  // the big batch's current buffer of b stays the current one
+  const double *src = sm.sel[t] ? mini.buf1 : mini.buf0;
+  for (int r = blockIdx.y; r < N * 17; r += gridDim.y) dst[size_t(r) * B + b] = src[size_t(r) * m + t];
+  for (int r = blockIdx.y; r < N * 4; r += gridDim.y) big.gk[size_t(r) * B + b] = mini.gk[size_t(r) * m + t];
+  for (int r = blockIdx.y; r < N * 48; r += gridDim.y) big.gK[size_t(r) * B + b] = mini.gK[size_t(r) * m + t];
+  for (int r = blockIdx.y; r < sb.hist_cap; r += gridDim.y)
+    if (sb.cost_hist) sb.cost_hist[size_t(r) * B + b] = sm.cost_hist[size_t(r) * m + t];
+  if (blockIdx.y != 0) return;
+  sb.cost[b] = sm.cost[t]; sb.new_cost[b] = sm.new_cost[t]; sb.qutk[b] = sm.qutk[t]; sb.ktquuk[b] = sm.ktquuk[t];
+  sb.alpha[b] = sm.alpha[t];
+  sb.ls_iter[b] = sm.ls_iter[t]; sb.status[b] = sm.status[t]; sb.bwd[b] = sm.bwd[t]; sb.rollouts[b] = sm.rollouts[t];
+  sb.ndebug[b] = sm.ndebug[t]; sb.phase[b] = sm.phase[t]; sb.accepted_iter[b] = sm.accepted_iter[t];
+}
 // ILQRDebug capture (ilqr.hh:78-80): copy the trajectory accepted in iteration `iter`.
 __global__ void k_debug_capture(Problem pr, SolveState st, const int *list, int n, int iter, double *debug /*[cap][N*17][B]*/, int cap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -503,3 +503,37 @@ def test_rollout_kernels_agree(monkeypatch):
     r2, r3 = s2.solve(d2[None], d2, hist_cap=100), s3.solve(d2[None], d2, hist_cap=100)
     assert np.array_equal(r2["results"], r3["results"]) and np.array_equal(r2["traj"], r3["traj"])
     assert np.array_equal(r2["cost_history"], r3["cost_history"])
+
+
+def test_tail_compaction_is_bit_identical(O, monkeypatch):
+    """When few problems are left they are moved into a dense mini-batch (k_tail_gather / k_tail_scatter).
+    Same kernels on the same values: every output equals the uncompacted solve bit for bit, for a shared and
+    for per-problem desired trajectories, with the sequential and the parallel line search; and the compacted
+    solve still matches the oracle."""
+    import dataclasses
+
+    from quadrotorilqr_b200 import problems
+
+    model = problems.hover_model()
+    monkeypatch.setenv("QILQR_HI_THRESHOLD", "24")  # the production threshold (2048) needs a batch above it
+    for opts in (problems.default_options(False),
+                 dataclasses.replace(problems.default_options(False), num_parallel_alphas=4, symmetrize_vxx=True)):
+        s_on = make_solver(model, opts)
+        monkeypatch.setenv("QILQR_TAIL_COMPACTION", "0")
+        s_off = make_solver(model, opts)
+        monkeypatch.delenv("QILQR_TAIL_COMPACTION")
+        B, N = 150, 40
+        desired, initial = hover_batch(s_on, B, N, seed=11)
+        per_problem = np.repeat(desired[None], B, axis=0)
+        per_problem[:, 20:, 1:4] += np.random.default_rng(2).uniform(-0.5, 0.5, (B, 1, 3))
+        for des in (desired, per_problem):
+            a = s_on.solve(initial, des, want_gains=True, hist_cap=100)
+            b = s_off.solve(initial, des, want_gains=True, hist_cap=100)
+            assert np.array_equal(a["results"], b["results"])
+            assert a["results"]["backward_passes"].max() > a["results"]["backward_passes"].min() + 3  # a real tail
+            for key in ("traj", "k", "K", "cost_history"):
+                assert np.array_equal(a[key], b[key]), key
+    s = make_solver(model, problems.default_options(False))
+    cfg = oracle_config(O, model, problems.default_options(False))
+    desired, initial = hover_batch(s, 120, 40, seed=4)
+    check_solve_against_oracle(O, s, cfg, desired, initial)
