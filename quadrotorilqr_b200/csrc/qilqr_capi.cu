@@ -66,6 +66,7 @@ struct qilqr_solver {
   int seq = 0;                       // sequence number of the last compaction (see wait_counts)
   int lists_B = 0;                   // batch the list buffer is laid out for
   int hi_threshold = 2048;           // switch to stream_hi when at most this many problems are active
+  int bulk_poll_us = 0;              // QILQR_BULK_POLL_US: sleep this long between polls while on the bulk stream (0: spin)
   std::string last_error;
   int64_t launches = 0;
   qilqr_solve_stats_t stats{};
@@ -247,12 +248,17 @@ int wait_counts(qilqr_solver *S, cudaStream_t st) {
     return QILQR_OK;
   }
   volatile int *seq = S->h_counts + 2;
-  for (unsigned spins = 0; *seq != S->seq; ++spins) {
-    if ((spins & 0x3ff) == 0x3ff) {
+  // Tail (high-priority stream): the wait is tens of microseconds and on the critical path -> spin.
+  // Bulk: the kernels ahead take milliseconds -> sleep between polls, so that many pipelined handles do not
+  // need a core each.
+  const bool spin = (st == S->stream_hi) || S->bulk_poll_us <= 0;
+  for (unsigned polls = 0; *seq != S->seq; ++polls) {
+    if ((polls & (spin ? 0x3ffu : 0x3fu)) == (spin ? 0x3ffu : 0x3fu)) {
       const cudaError_t e = cudaStreamQuery(st);
       if (e != cudaSuccess && e != cudaErrorNotReady) QCUDA(S, e);
     }
-    std::this_thread::yield();
+    if (spin) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(S->bulk_poll_us));
   }
   std::atomic_thread_fence(std::memory_order_acquire);  // the list lengths are read after the sequence word
   return QILQR_OK;
@@ -633,6 +639,7 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   int prio_least = 0, prio_greatest = 0;
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   if (const char *e = std::getenv("QILQR_HI_THRESHOLD")) S->hi_threshold = std::atoi(e);
+  if (const char *e = std::getenv("QILQR_BULK_POLL_US")) S->bulk_poll_us = std::atoi(e);
   if (cudaStreamCreateWithPriority(&S->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
       cudaStreamCreateWithPriority(&S->stream_hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaEventCreateWithFlags(&S->ev_switch, cudaEventDisableTiming) != cudaSuccess ||
