@@ -23,6 +23,7 @@
 #include "qilqr_backward_g4.cuh"
 #include "qilqr_backward_split.cuh"
 #include "qilqr_backward_dense.cuh"
+#include "qilqr_tail_persistent.cuh"
 
 using namespace qilqr;
 
@@ -87,6 +88,7 @@ struct qilqr_solver {
   // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
   DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map;
   bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
+  bool persistent_tail = false;  // EXPERIMENTAL, QILQR_PERSISTENT_TAIL=1: one kernel for the whole compacted tail
   int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
   int *d_counts = nullptr;
 };
@@ -423,6 +425,18 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         B_eff = m;
         m_tail = m;
         compacted = true;
+        if (S->persistent_tail && P_alpha <= 1 && !S->generic_path && !S->force_t1 && S->split_backward) {
+          // the rest of the solve for these m problems in one launch (qilqr_tail_persistent.cuh)
+          const int tiles = (m + 7) / 8;
+          const bool dq = !S->q_block_diagonal;
+          if (S->rec_d.ensure(sizeof(double) * size_t(tiles) * 8 * N * g4::rect(dq)) != cudaSuccess)
+            return fail(S, QILQR_ERR_OUT_OF_MEMORY, "out of device memory for the linearisation records");
+          const size_t smem = sizeof(double) * tp::smem_doubles(dq);
+          if (dq) k_tail_persistent<true><<<tiles, 96, smem, st_>>>(S->p, pm, sm, S->rec_d.as<double>(), m, i);
+          else k_tail_persistent<false><<<tiles, 96, smem, st_>>>(S->p, pm, sm, S->rec_d.as<double>(), m, i);
+          ++S->launches;
+          break;
+        }
       }
     }
     const bool wide = P_alpha > 1 && i > 0;  // iteration 0 is an unconditional full step (ilqr.hh:70-73)
@@ -629,6 +643,7 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   }
   if (const char *e = std::getenv("QILQR_ROLLOUT")) S->rollout_ws = std::string(e) != "thread";
   if (const char *e = std::getenv("QILQR_TAIL_COMPACTION")) S->tail_compaction = std::atoi(e) != 0;
+  if (const char *e = std::getenv("QILQR_PERSISTENT_TAIL")) S->persistent_tail = std::atoi(e) != 0;
   if (const char *e = std::getenv("QILQR_WS_THRESHOLD")) S->ws_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);

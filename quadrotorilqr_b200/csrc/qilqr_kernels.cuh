@@ -261,16 +261,11 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
 // acceleration; every value is computed by the same instruction sequence as in k_rollout, so the two
 // kernels agree bit for bit (tests/test_gpu_parity.py::test_rollout_kernels_agree).
 // ---------------------------------------------------------------------------
-#ifndef QILQR_WS_MINB
-#define QILQR_WS_MINB 2
-#endif
-__global__ void __launch_bounds__(96, QILQR_WS_MINB) k_rollout_ws(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
-  __shared__ double s_pose[2][7][32], s_vel[6][32], s_u[4][32];
-  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  const int t0 = blockIdx.x * 32 + lane;
-  const bool valid = t0 < a.n;
-  const int t = valid ? t0 : a.n - 1;  // idle lanes shadow the last problem (they must reach the barriers) and write nothing
-  const int b = a.list ? a.list[t] : t;
+// The body shared by k_rollout_ws and the persistent tail kernel: every thread of a 96-thread CTA calls it (it
+// contains CTA barriers); `lane` selects the problem slot, `role` the warp's part, `b` the problem (idle slots
+// shadow a valid problem with valid = false: they must reach the barriers and write nothing).
+QD void rollout_ws_run(const DeviceParams &p, const RolloutArgs &a, const int lane, const int role, const bool valid,
+                       const int b, double (*s_pose)[7][32], double (*s_vel)[32], double (*s_u)[32]) {
   const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
   const int bd = (Bd == 1) ? 0 : b;
   const double *cur;
@@ -390,6 +385,17 @@ __global__ void __launch_bounds__(96, QILQR_WS_MINB) k_rollout_ws(const __grid_c
     return;
   }
   rollout_finish(p, a, b, alpha, cost);
+}
+#ifndef QILQR_WS_MINB
+#define QILQR_WS_MINB 2
+#endif
+__global__ void __launch_bounds__(96, QILQR_WS_MINB) k_rollout_ws(const __grid_constant__ DeviceParams p, const __grid_constant__ RolloutArgs a) {
+  __shared__ double s_pose[2][7][32], s_vel[6][32], s_u[4][32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * 32 + lane;
+  const bool valid = t0 < a.n;
+  const int t = valid ? t0 : a.n - 1;
+  rollout_ws_run(p, a, lane, role, valid, a.list ? a.list[t] : t, s_pose, s_vel, s_u);
 }
 
 // ---------------------------------------------------------------------------

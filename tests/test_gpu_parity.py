@@ -537,3 +537,49 @@ def test_tail_compaction_is_bit_identical(O, monkeypatch):
     cfg = oracle_config(O, model, problems.default_options(False))
     desired, initial = hover_batch(s, 120, 40, seed=4)
     check_solve_against_oracle(O, s, cfg, desired, initial)
+
+
+def test_persistent_tail_matches_host_loop(O, monkeypatch):
+    """The experimental persistent tail kernel (QILQR_PERSISTENT_TAIL=1: one launch runs the rest of solve() for the
+    compacted stragglers) executes the same device code as the host-driven loop: identical decisions; values equal
+    up to the compiler's FMA contraction, which differs between kernels.  Block-diagonal and coupled Q, shared and
+    per-problem desired trajectories, ragged tiles, line-search exhaustion; and it matches the oracle."""
+    import dataclasses
+
+    from quadrotorilqr_b200 import problems
+
+    def pair(model, opts):
+        monkeypatch.setenv("QILQR_PERSISTENT_TAIL", "1")
+        on = make_solver(model, opts)
+        monkeypatch.delenv("QILQR_PERSISTENT_TAIL")
+        return on, make_solver(model, opts)
+
+    monkeypatch.setenv("QILQR_HI_THRESHOLD", "21")  # not a multiple of 8: the last tile is ragged
+    base = problems.hover_model()
+    rng = np.random.default_rng(5)
+    A = rng.uniform(-0.3, 0.3, (12, 12))
+    coupled = dict(base, Q=base["Q"] + A @ A.T)
+    for model in (base, coupled):
+        s_on, s_off = pair(model, problems.default_options(False))
+        B, N = 150, 40
+        desired, initial = hover_batch(s_on, B, N, seed=11)
+        per_problem = np.repeat(desired[None], B, axis=0)
+        per_problem[:, 20:, 1:4] += rng.uniform(-0.5, 0.5, (B, 1, 3))
+        for des in (desired, per_problem):
+            a = s_on.solve(initial, des, want_gains=True, hist_cap=100)
+            b = s_off.solve(initial, des, want_gains=True, hist_cap=100)
+            assert a["results"]["backward_passes"].max() > a["results"]["backward_passes"].min() + 3  # a real tail
+            for f in ("status", "backward_passes", "rollouts", "num_debug"):
+                assert np.array_equal(a["results"][f], b["results"][f]), f
+            for key in ("traj", "k", "K", "cost_history"):
+                assert_close(a[key], b[key], rtol=1e-11, what=key)
+    s_on, _ = pair(base, problems.default_options(False))
+    cfg = oracle_config(O, base, problems.default_options(False))
+    desired, initial = hover_batch(s_on, 120, 40, seed=4)
+    check_solve_against_oracle(O, s_on, cfg, desired, initial)
+    tight = dataclasses.replace(problems.default_options(False))
+    tight.line_search_params = dataclasses.replace(tight.line_search_params, max_iters=1, desired_reduction_frac=0.999)
+    s_on, s_off = pair(base, tight)
+    a, b = s_on.solve(initial, desired), s_off.solve(initial, desired)
+    assert np.array_equal(a["results"]["status"], b["results"]["status"]) and (a["results"]["status"] == 4).any()
+    assert_close(a["traj"], b["traj"], rtol=1e-11, what="traj")
