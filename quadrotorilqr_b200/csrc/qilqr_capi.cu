@@ -362,6 +362,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     d_K = S->gK.as<double>();
   }
   cudaStream_t st_ = S->stream;
+  S->cur = st_;  // (an earlier solve that failed in its tail may have left the high-priority stream selected)
   Problem pr{B, N, Bd, d_traj, S->buf1.as<double>(), d_desired, d_k, d_K};
   SolveState st = make_state(S, B, d_hist, d_hist ? hist_cap : 0);
   int *listA[2] = {S->lists.as<int>(), S->lists.as<int>() + B};
