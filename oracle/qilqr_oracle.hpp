@@ -16,6 +16,10 @@
 // cost_test.cc:27-151) and scipy expm/logm cross-checks of the Lie functions
 // (tests/test_oracle_*.py).  No reference test pins an N>3 solve, so beyond
 // those cases this oracle is "parity unpinned" -- it IS the golden source.
+// Its formulas are additionally checked against an independent 50-digit
+// restatement of one full iLQR iteration (matrix exponential / logarithm,
+// numerically differentiated; tests/test_oracle_mpmath.py: agreement 1e-14),
+// which bounds its rounding but is no substitute for the literal reference.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may use anything under oracle/.
