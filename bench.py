@@ -195,6 +195,11 @@ def main():
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         return reference_arm(args, rank, world)
+    # Two streams per handle: with the default 8 hardware queues, streams that share a queue serialise (a tail kernel
+    # waits for another handle's bulk kernel to be dispatched).  Must be set before the CUDA context exists.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    if args.pipeline > 8:  # more host threads than a small box has cores to spare: sleep-poll while a batch is in its bulk
+        os.environ.setdefault("QILQR_BULK_POLL_US", "30")
 
     import torch
 
@@ -460,7 +465,8 @@ def main():
                    "parallelism": f"{world} independent shard(s), one process per GPU",
                    **({"model_variant": f"{args.model_variant} (NOT the BASELINE model: see --model-variant)"}
                       if args.model_variant else {}),
-                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream each), "
+                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream pair each, "
+                               f"CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')}), "
                                f"started {1e3 * stagger_s:.1f} ms apart; each step is one full batch"},
         "serial_ms_per_step": serial_ms,
         "serial_value": (converged / (serial_ms * 1e-3)) if serial_ms else None,

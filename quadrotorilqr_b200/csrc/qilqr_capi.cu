@@ -68,6 +68,8 @@ struct qilqr_solver {
   int lists_B = 0;                   // batch the list buffer is laid out for
   int hi_threshold = 2048;           // switch to stream_hi when at most this many problems are active
   int bulk_poll_us = 0;              // QILQR_BULK_POLL_US: sleep this long between polls while on the bulk stream (0: spin)
+  bool tail_stream = true;           // QILQR_TAIL_STREAM=0: the tail stays on the handle's main stream (one stream per handle)
+  bool in_tail = false;              // the current solve has entered its latency-bound tail
   std::string last_error;
   int64_t launches = 0;
   qilqr_solve_stats_t stats{};
@@ -253,7 +255,7 @@ int wait_counts(qilqr_solver *S, cudaStream_t st) {
   // Tail (high-priority stream): the wait is tens of microseconds and on the critical path -> spin.
   // Bulk: the kernels ahead take milliseconds -> sleep between polls, so that many pipelined handles do not
   // need a core each.
-  const bool spin = (st == S->stream_hi) || S->bulk_poll_us <= 0;
+  const bool spin = S->in_tail || S->bulk_poll_us <= 0;
   for (unsigned polls = 0; *seq != S->seq; ++polls) {
     if ((polls & (spin ? 0x3ffu : 0x3fu)) == (spin ? 0x3ffu : 0x3fu)) {
       const cudaError_t e = cudaStreamQuery(st);
@@ -363,6 +365,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   }
   cudaStream_t st_ = S->stream;
   S->cur = st_;  // (an earlier solve that failed in its tail may have left the high-priority stream selected)
+  S->in_tail = false;
   Problem pr{B, N, Bd, d_traj, S->buf1.as<double>(), d_desired, d_k, d_K};
   SolveState st = make_state(S, B, d_hist, d_hist ? hist_cap : 0);
   int *listA[2] = {S->lists.as<int>(), S->lists.as<int>() + B};
@@ -393,11 +396,14 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     if (!on_hi && n_active <= S->hi_threshold && B > S->hi_threshold) {
       // Few problems left: every further iteration is a chain of tiny, latency-bound launches.  Move them
       // to the high-priority stream so that they are not queued behind another handle's bulk kernels.
-      cudaEventRecord(S->ev_switch, st_);
-      cudaStreamWaitEvent(S->stream_hi, S->ev_switch, 0);
-      st_ = S->stream_hi;
-      S->cur = st_;
+      if (S->tail_stream) {
+        cudaEventRecord(S->ev_switch, st_);
+        cudaStreamWaitEvent(S->stream_hi, S->ev_switch, 0);
+        st_ = S->stream_hi;
+        S->cur = st_;
+      }
       on_hi = true;
+      S->in_tail = true;
       t_switch = std::chrono::steady_clock::now();
       if (S->tail_compaction && !capture_debug && active) {
         // ... and into a dense mini-batch: m problems, pitch m instead of B
@@ -528,11 +534,12 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     k_collect<<<grid, 128, 0, st_>>>(pr_big, st_big.sel);
   }
   S->launches += 2;
-  if (on_hi) {  // rejoin the solver's main stream
+  if (on_hi && S->tail_stream) {  // rejoin the solver's main stream
     cudaEventRecord(S->ev_switch, st_);
     cudaStreamWaitEvent(S->stream, S->ev_switch, 0);
     S->cur = S->stream;
   }
+  S->in_tail = false;
   QCUDA(S, cudaStreamSynchronize(S->stream));
   QCUDA(S, cudaGetLastError());
   S->stats.kernel_launches = S->launches - launches0;
@@ -656,6 +663,7 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   if (const char *e = std::getenv("QILQR_HI_THRESHOLD")) S->hi_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_BULK_POLL_US")) S->bulk_poll_us = std::atoi(e);
+  if (const char *e = std::getenv("QILQR_TAIL_STREAM")) S->tail_stream = std::atoi(e) != 0;
   if (cudaStreamCreateWithPriority(&S->stream, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
       cudaStreamCreateWithPriority(&S->stream_hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaEventCreateWithFlags(&S->ev_switch, cudaEventDisableTiming) != cudaSuccess ||
