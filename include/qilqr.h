@@ -124,6 +124,9 @@ int qilqr_set_options(qilqr_solver_t *solver, const qilqr_options_t *options);
 enum { QILQR_MODEL_REFERENCE = 0, QILQR_MODEL_RK4 = 1, QILQR_MODEL_CORIOLIS = 2, QILQR_MODEL_GENERIC = 4 };
 int qilqr_set_model_variant(qilqr_solver_t *solver, int model_flags);
 const char *qilqr_error_string(int err);
+/* How this build rounds: "production: explicit fused multiply-adds, reciprocal multiplies" or
+ * "strict: no fused multiply-adds, true divisions (-DQILQR_STRICT)"; both are compiled with -fmad=false. */
+const char *qilqr_build_info(void);
 const char *qilqr_last_error_message(const qilqr_solver_t *solver);
 /* Number of this library's kernels launched by the solver so far (for bench.py's gpu_launches). */
 int64_t qilqr_kernel_launch_count(const qilqr_solver_t *solver);
@@ -229,7 +232,9 @@ int qilqr_mpc_run_device(qilqr_solver_t *solver, int steps, int batch, int n_kno
 
 /* Aggregate counters of the last qilqr_solve_* call. */
 typedef struct {
-  int64_t solver_iterations;   /* outer iterations issued (max over problems) */
+  int64_t solver_iterations;   /* super-steps sequenced by the host (backward pass + rollout + compaction over the
+                                  problem lists); the iterations the persistent tail kernel runs on its own once few
+                                  problems are alive are not counted */
   int64_t problem_iterations;  /* sum over problems of backward passes */
   int64_t problem_rollouts;    /* sum over problems of rollouts */
   int64_t kernel_launches;     /* kernels launched by this call */

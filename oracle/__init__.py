@@ -20,7 +20,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libqilqr_oracle.so")
+# QORACLE_LIB=plibm selects the build whose sin / cos / atan2 come from the portable implementation shared with
+# the STRICT CUDA build (bit-for-bit comparisons only; oracle/Makefile)
+_LIB_NAME = "libqilqr_oracle_plibm.so" if os.environ.get("QORACLE_LIB", "") == "plibm" else "libqilqr_oracle.so"
+_LIB_PATH = os.path.join(_HERE, _LIB_NAME)
 
 STATUS_CONVERGED_EXPECTED = 1
 STATUS_CONVERGED_ACTUAL = 2
@@ -73,12 +76,12 @@ RESULT_DTYPE = np.dtype(
 def build(force: bool = False) -> str:
     """Compile the oracle (g++ -O2 -ffp-contract=off).  Building is not using."""
     src = [os.path.join(_HERE, f) for f in ("qilqr_oracle_capi.cc", "qilqr_oracle.hpp")]
-    stale = force or not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src
-    )
+    src.append(os.path.join(_HERE, "..", "quadrotorilqr_b200", "csrc", "qilqr_portable_libm.h"))
+    targets = [os.path.join(_HERE, n) for n in ("libqilqr_oracle.so", "libqilqr_oracle_plibm.so")]
+    stale = force or any(not os.path.exists(t) or any(os.path.getmtime(s) > os.path.getmtime(t) for s in src)
+                         for t in targets)
     if stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libqilqr_oracle.so"],
-                              stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "-j2", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 

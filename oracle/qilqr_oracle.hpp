@@ -31,6 +31,9 @@
 // with a FLOP-counting scalar (oracle_capi.cc: qoracle_count_flops).
 // =============================================================================
 #pragma once
+#ifdef QORACLE_PORTABLE_LIBM
+#include "../quadrotorilqr_b200/csrc/qilqr_portable_libm.h"
+#endif
 #include <cmath>
 #include <cfloat>
 #include <cstddef>
@@ -79,10 +82,19 @@ inline double to_double(CountedDouble a) { return a.v; }
 inline double to_double(double a) { return a; }
 
 using std::abs;
+using std::sqrt;
+#ifdef QORACLE_PORTABLE_LIBM
+// Bit-for-bit comparison builds only (liboracle ..._plibm.so): sin / cos / atan2 from the portable implementation
+// that the STRICT CUDA build can be compiled with too (quadrotorilqr_b200/csrc/qilqr_portable_libm.h), instead of
+// the C library's.  Everything else is unchanged.
+using qilqr_plibm::atan2;
+using qilqr_plibm::cos;
+using qilqr_plibm::sin;
+#else
 using std::atan2;
 using std::cos;
 using std::sin;
-using std::sqrt;
+#endif
 
 // ----------------------------------------------------------------------------
 // Minimal fixed-size dense matrix (row-major storage; storage order is not

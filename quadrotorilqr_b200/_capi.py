@@ -91,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "qilqr_unpack_trajectory_device", "qilqr_rollout_constant_control_device",
     "qilqr_last_solve_stats", "qilqr_set_profiling", "qilqr_measure_fp64_peak",
     "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
-    "qilqr_set_model_variant",
+    "qilqr_set_model_variant", "qilqr_build_info",
 ]
 
 MODEL_REFERENCE = 0
@@ -100,17 +100,27 @@ MODEL_CORIOLIS = 2
 MODEL_GENERIC = 4
 
 
+STRICT_LIB_PATH = os.path.join(_HERE, "libqilqr_b200_strict.so")  # -DQILQR_STRICT build (csrc/Makefile)
+PLIBM_LIB_PATH = os.path.join(_HERE, "libqilqr_b200_strict_plibm.so")  # ... + portable sin/cos/atan2
+
+
 def build(force: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (cross-compiles without a GPU)."""
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (cross-compiles without a GPU).
+
+    Builds the production library and the opt-in STRICT build (no fused multiply-adds, true divisions;
+    load it with ``QILQR_LIB=quadrotorilqr_b200/libqilqr_b200_strict.so``)."""
     csrc = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(_HERE, "..", "include", "qilqr.h"))
-    stale = force or not os.path.exists(LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs
-    )
+    targets = [os.path.join(_HERE, "libqilqr_b200.so"), STRICT_LIB_PATH, PLIBM_LIB_PATH]
+    stale = force or any(not os.path.exists(t) or any(os.path.getmtime(s) > os.path.getmtime(t) for s in srcs)
+                         for t in targets)
     if stale:
-        subprocess.check_call(["make", "-C", csrc, "-B"], stdout=subprocess.DEVNULL,
-                              stderr=subprocess.DEVNULL)
+        r = subprocess.run(["make", "-C", csrc, "-B", "-j3", "all"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"building the CUDA library failed (make -C {csrc}, exit code {r.returncode}):\n"
+                               + r.stdout[-4000:])
     return LIB_PATH
 
 
@@ -127,12 +137,13 @@ def lib() -> C.CDLL:
                 "g.build()'` (there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
         L.qilqr_error_string.restype = C.c_char_p
+        L.qilqr_build_info.restype = C.c_char_p
         L.qilqr_last_error_message.restype = C.c_char_p
         L.qilqr_kernel_launch_count.restype = C.c_int64
         L.qilqr_stream.restype = C.c_void_p
         for name in EXPORTED_SYMBOLS:
             fn = getattr(L, name)
-            if name not in ("qilqr_error_string", "qilqr_last_error_message",
+            if name not in ("qilqr_error_string", "qilqr_last_error_message", "qilqr_build_info",
                             "qilqr_kernel_launch_count", "qilqr_stream", "qilqr_destroy"):
                 fn.restype = C.c_int
         L.qilqr_destroy.restype = None

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
 #pragma unroll
       for (int k = 1; k < 12; ++k) {
         const double av = RA(k, r);
-        m0 = fma(av, Vc[3 * k], m0); m1 = fma(av, Vc[3 * k + 1], m1); m2 = fma(av, Vc[3 * k + 2], m2);
+        m0 = QFMA(av, Vc[3 * k], m0); m1 = QFMA(av, Vc[3 * k + 1], m1); m2 = QFMA(av, Vc[3 * k + 2], m2);
       }
       Mc[3 * r] = m0; Mc[3 * r + 1] = m1; Mc[3 * r + 2] = m2;
     }
@@ -150,10 +150,10 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double bv = RB(k, j);
-        BtVc[3 * j] = fma(bv, Vc[3 * k], BtVc[3 * j]);
-        BtVc[3 * j + 1] = fma(bv, Vc[3 * k + 1], BtVc[3 * j + 1]);
-        BtVc[3 * j + 2] = fma(bv, Vc[3 * k + 2], BtVc[3 * j + 2]);
-        Qu[j] = fma(bv, vx[k], Qu[j]);
+        BtVc[3 * j] = QFMA(bv, Vc[3 * k], BtVc[3 * j]);
+        BtVc[3 * j + 1] = QFMA(bv, Vc[3 * k + 1], BtVc[3 * j + 1]);
+        BtVc[3 * j + 2] = QFMA(bv, Vc[3 * k + 2], BtVc[3 * j + 2]);
+        Qu[j] = QFMA(bv, vx[k], Qu[j]);
       }
 #pragma unroll
     for (int j = 0; j < 4; ++j) Qu[j] = rec[(D_CU + j) * 8] + Qu[j];  // Q.u = C.u + J_u^T v_x
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
     for (int j = 0; j < 3; ++j) {
       double sx = Ac[j] * vx[0];
 #pragma unroll
-      for (int k = 1; k < 12; ++k) sx = fma(Ac[3 * k + j], vx[k], sx);
+      for (int k = 1; k < 12; ++k) sx = QFMA(Ac[3 * k + j], vx[k], sx);
       Qxc[j] = rec[(D_CX + 3 * c + j) * 8] + sx;  // Q.x = C.x + J_x^T v_x
     }
     __syncwarp();  // the exchange area is free: every lane has finished step 4 of the previous knot
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
 #pragma unroll
       for (int k = 1; k < 12; ++k) {
         const double mv = xch[E_M + 12 * r + k];
-        s0 = fma(mv, Ac[3 * k], s0); s1 = fma(mv, Ac[3 * k + 1], s1); s2 = fma(mv, Ac[3 * k + 2], s2);
+        s0 = QFMA(mv, Ac[3 * k], s0); s1 = QFMA(mv, Ac[3 * k + 1], s1); s2 = QFMA(mv, Ac[3 * k + 2], s2);
       }
       // C.xx[r][3c + j]: rows 0..5 from the pp | pv blocks of the record, rows 6..11 from the vp block | 2 Q_vv table
       const double *cxx = (r < 6) ? ctop + 48 * r : cbot + cbot_rs * (r - 6);
@@ -215,17 +215,17 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
         for (int i2 = 0; i2 < 3; ++i2) {
           const double mv = Mrow[12 * i2 + k];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) Qxuc[4 * i2 + j] = (k == 0) ? mv * bv[j] : fma(mv, bv[j], Qxuc[4 * i2 + j]);
+          for (int j = 0; j < 4; ++j) Qxuc[4 * i2 + j] = (k == 0) ? mv * bv[j] : QFMA(mv, bv[j], Qxuc[4 * i2 + j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const double tv = xch[E_BTV + 12 * j + k];
 #pragma unroll
-          for (int l = 0; l < 4; ++l) Quu[4 * j + l] = (k == 0) ? tv * bv[l] : fma(tv, bv[l], Quu[4 * j + l]);
+          for (int l = 0; l < 4; ++l) Quu[4 * j + l] = (k == 0) ? tv * bv[l] : QFMA(tv, bv[l], Quu[4 * j + l]);
         }
       }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) Quu[e] = 2.0 * p.R[e] + Quu[e];  // C.uu = 2 R (cost.hh:54)
+      for (int e = 0; e < 16; ++e) Quu[e] = QFMA(2.0, p.R[e], Quu[e]);  // C.uu = 2 R (cost.hh:54)
       if (p.quu_reg != 0.0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) Quu[5 * j] += p.quu_reg;
@@ -264,14 +264,14 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
       for (int l = 0; l < 4; ++l) {
         double acc = Kc[i2] * Quu[l];
 #pragma unroll
-        for (int j = 1; j < 4; ++j) acc = fma(Kc[3 * j + i2], Quu[4 * j + l], acc);
+        for (int j = 1; j < 4; ++j) acc = QFMA(Kc[3 * j + i2], Quu[4 * j + l], acc);
         KtQc[4 * i2 + l] = acc;
       }
 #pragma unroll
     for (int i2 = 0; i2 < 3; ++i2) {
       double acc = KtQc[4 * i2] * kk[0];
 #pragma unroll
-      for (int l = 1; l < 4; ++l) acc = fma(KtQc[4 * i2 + l], kk[l], acc);
+      for (int l = 1; l < 4; ++l) acc = QFMA(KtQc[4 * i2 + l], kk[l], acc);
       xch[E_VX + 3 * c + i2] = Qxc[i2] - acc;  // v_x = Q.x - (K^T Q.uu) k
 #pragma unroll
       for (int l = 0; l < 4; ++l) xch[E_KTQ + 4 * (3 * c + i2) + l] = KtQc[4 * i2 + l];
@@ -279,19 +279,19 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
     {  // expected cost reduction terms (ilqr.hh:136-140)
       double acc = Qu[0] * kk[0];
 #pragma unroll
-      for (int j = 1; j < 4; ++j) acc = fma(Qu[j], kk[j], acc);
+      for (int j = 1; j < 4; ++j) acc = QFMA(Qu[j], kk[j], acc);
       QuTk = QuTk + acc;
       double z[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         double sz = kk[0] * Quu[l];
 #pragma unroll
-        for (int j = 1; j < 4; ++j) sz = fma(kk[j], Quu[4 * j + l], sz);
+        for (int j = 1; j < 4; ++j) sz = QFMA(kk[j], Quu[4 * j + l], sz);
         z[l] = sz;
       }
       double acc2 = z[0] * kk[0];
 #pragma unroll
-      for (int l = 1; l < 4; ++l) acc2 = fma(z[l], kk[l], acc2);
+      for (int l = 1; l < 4; ++l) acc2 = QFMA(z[l], kk[l], acc2);
       kTQuuk = kTQuuk + acc2;
     }
     __syncwarp();
@@ -304,9 +304,9 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         double acc = t0 * Kc[j];
-        acc = fma(t1, Kc[3 + j], acc);
-        acc = fma(t2, Kc[6 + j], acc);
-        acc = fma(t3, Kc[9 + j], acc);
+        acc = QFMA(t1, Kc[3 + j], acc);
+        acc = QFMA(t2, Kc[6 + j], acc);
+        acc = QFMA(t3, Kc[9 + j], acc);
         Vc[3 * r + j] = Qxxc[3 * r + j] - acc;
       }
     }
@@ -329,25 +329,7 @@ __global__ void __launch_bounds__(32) k_riccati_dense(const __grid_constant__ De
   }
 
   if (!valid || c != 0) return;
-  if (!a.solve_mode) {
-    a.terms_out[2 * size_t(b)] = QuTk;
-    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
-    return;
-  }
-  const SolveState &st = a.st;
-  st.qutk[b] = QuTk;
-  st.ktquuk[b] = kTQuuk;
-  st.bwd[b] += 1;
-  const double cost = st.cost[b];
-  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
-  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
-    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
-    st.phase[b] = PHASE_DONE;
-  } else {
-    st.alpha[b] = 1.0;
-    st.ls_iter[b] = 0;
-    st.phase[b] = a.search_phase;
-  }
+  backward_finish(p, a, b, QuTk, kTQuuk);
 }
 
 }  // namespace qilqr

@@ -55,22 +55,23 @@ QD void st9s(double *s, const double *r) {
 #pragma unroll
   for (int e = 0; e < 9; ++e) s[e * RS] = r[e];
 }
-// C += hat(t) * M
+// C += hat(t) * M, term by term in the order of the dense product (row i of hat(t) = [0 -t2 t1; t2 0 -t0; -t1 t0 0];
+// the structural zero of each row contributes an exact zero and is skipped)
 QD void m3_hat_madd(const double *t, const double *M, double *C) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    C[0 + j] += fma(t[1], M[6 + j], -(t[2] * M[3 + j]));
-    C[3 + j] += fma(t[2], M[0 + j], -(t[0] * M[6 + j]));
-    C[6 + j] += fma(t[0], M[3 + j], -(t[1] * M[0 + j]));
+    C[0 + j] = QFMA(t[1], M[6 + j], QFMA(-t[2], M[3 + j], C[0 + j]));
+    C[3 + j] = QFMA(-t[0], M[6 + j], QFMA(t[2], M[0 + j], C[3 + j]));
+    C[6 + j] = QFMA(t[0], M[3 + j], QFMA(-t[1], M[0 + j], C[6 + j]));
   }
 }
-// C += M * hat(w)
+// C += M * hat(w), likewise (column j of hat(w) = [0 w2 -w1; -w2 0 w0; w1 -w0 0])
 QD void m3_madd_hat(const double *M, const double *w, double *C) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    C[3 * i + 0] += fma(M[3 * i + 1], w[2], -(M[3 * i + 2] * w[1]));
-    C[3 * i + 1] += fma(M[3 * i + 2], w[0], -(M[3 * i + 0] * w[2]));
-    C[3 * i + 2] += fma(M[3 * i + 0], w[1], -(M[3 * i + 1] * w[0]));
+    C[3 * i + 0] = QFMA(M[3 * i + 2], -w[1], QFMA(M[3 * i + 1], w[2], C[3 * i + 0]));
+    C[3 * i + 1] = QFMA(M[3 * i + 2], w[0], QFMA(M[3 * i + 0], -w[2], C[3 * i + 1]));
+    C[3 * i + 2] = QFMA(M[3 * i + 1], -w[0], QFMA(M[3 * i + 0], w[1], C[3 * i + 2]));
   }
 }
 
@@ -100,7 +101,7 @@ QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, 
     for (int j = 0; j < 12; ++j) {
       double s = (2.0 * dx[0]) * p.Q[j];
 #pragma unroll
-      for (int i = 1; i < 12; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+      for (int i = 1; i < 12; ++i) s = QFMA(2.0 * dx[i], p.Q[12 * i + j], s);
       y[j] = s;
     }
   } else {
@@ -108,11 +109,11 @@ QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, 
     for (int j = 0; j < 6; ++j) {
       double s = (2.0 * dx[0]) * p.Q[j];
 #pragma unroll
-      for (int i = 1; i < 6; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+      for (int i = 1; i < 6; ++i) s = QFMA(2.0 * dx[i], p.Q[12 * i + j], s);
       y[j] = s;
       double s2 = (2.0 * dx[6]) * p.Q[72 + 6 + j];
 #pragma unroll
-      for (int i = 7; i < 12; ++i) s2 = fma(2.0 * dx[i], p.Q[12 * i + 6 + j], s2);
+      for (int i = 7; i < 12; ++i) s2 = QFMA(2.0 * dx[i], p.Q[12 * i + 6 + j], s2);
       y[6 + j] = s2;
     }
   }
@@ -126,7 +127,7 @@ QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, 
   for (int j = 0; j < 4; ++j) {
     double s = (2.0 * (u[0] - ud[0])) * p.R[j];
 #pragma unroll
-    for (int l = 1; l < 4; ++l) s = fma(2.0 * (u[l] - ud[l]), p.R[4 * l + j], s);
+    for (int l = 1; l < 4; ++l) s = QFMA(2.0 * (u[l] - ud[l]), p.R[4 * l + j], s);
     rec[L::cu(j) * RS] = s;
   }
   // C_xx = ((2 J^T) Q) J with J = blkdiag(J6, I), J6 = [[Ji, Qi], [0, Ji]]:
@@ -137,26 +138,26 @@ QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, 
     double Pa[PC], Pb[PC];  // rows i and 3+i of P
 #pragma unroll
     for (int j = 0; j < PC; ++j) {
-      Pa[j] = fma(2.0 * Ji[6 + i], p.Q[24 + j], fma(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
-      double s = fma(2.0 * Qi[6 + i], p.Q[24 + j], fma(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
-      s = fma(2.0 * Ji[i], p.Q[36 + j], s);
-      s = fma(2.0 * Ji[3 + i], p.Q[48 + j], s);
-      s = fma(2.0 * Ji[6 + i], p.Q[60 + j], s);
+      Pa[j] = QFMA(2.0 * Ji[6 + i], p.Q[24 + j], QFMA(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
+      double s = QFMA(2.0 * Qi[6 + i], p.Q[24 + j], QFMA(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
+      s = QFMA(2.0 * Ji[i], p.Q[36 + j], s);
+      s = QFMA(2.0 * Ji[3 + i], p.Q[48 + j], s);
+      s = QFMA(2.0 * Ji[6 + i], p.Q[60 + j], s);
       Pb[j] = s;
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      rec[L::cpp(i, j) * RS] = fma(Pa[2], Ji[6 + j], fma(Pa[1], Ji[3 + j], Pa[0] * Ji[j]));
-      rec[L::cpp(3 + i, j) * RS] = fma(Pb[2], Ji[6 + j], fma(Pb[1], Ji[3 + j], Pb[0] * Ji[j]));
-      double s = fma(Pa[2], Qi[6 + j], fma(Pa[1], Qi[3 + j], Pa[0] * Qi[j]));
-      s = fma(Pa[3], Ji[j], s);
-      s = fma(Pa[4], Ji[3 + j], s);
-      s = fma(Pa[5], Ji[6 + j], s);
+      rec[L::cpp(i, j) * RS] = QFMA(Pa[2], Ji[6 + j], QFMA(Pa[1], Ji[3 + j], Pa[0] * Ji[j]));
+      rec[L::cpp(3 + i, j) * RS] = QFMA(Pb[2], Ji[6 + j], QFMA(Pb[1], Ji[3 + j], Pb[0] * Ji[j]));
+      double s = QFMA(Pa[2], Qi[6 + j], QFMA(Pa[1], Qi[3 + j], Pa[0] * Qi[j]));
+      s = QFMA(Pa[3], Ji[j], s);
+      s = QFMA(Pa[4], Ji[3 + j], s);
+      s = QFMA(Pa[5], Ji[6 + j], s);
       rec[L::cpp(i, 3 + j) * RS] = s;
-      double s2 = fma(Pb[2], Qi[6 + j], fma(Pb[1], Qi[3 + j], Pb[0] * Qi[j]));
-      s2 = fma(Pb[3], Ji[j], s2);
-      s2 = fma(Pb[4], Ji[3 + j], s2);
-      s2 = fma(Pb[5], Ji[6 + j], s2);
+      double s2 = QFMA(Pb[2], Qi[6 + j], QFMA(Pb[1], Qi[3 + j], Pb[0] * Qi[j]));
+      s2 = QFMA(Pb[3], Ji[j], s2);
+      s2 = QFMA(Pb[4], Ji[3 + j], s2);
+      s2 = QFMA(Pb[5], Ji[6 + j], s2);
       rec[L::cpp(3 + i, 3 + j) * RS] = s2;
     }
     if (DENSEQ) {
@@ -176,11 +177,11 @@ QD void cost_to_record(const DeviceParams &p, const double *x, const double *u, 
       for (int k = 0; k < 6; ++k) Pr[k] = 2.0 * p.Q[12 * (6 + i) + k];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        rec[L::cvp(i, j) * RS] = fma(Pr[2], Ji[6 + j], fma(Pr[1], Ji[3 + j], Pr[0] * Ji[j]));
-        double s = fma(Pr[2], Qi[6 + j], fma(Pr[1], Qi[3 + j], Pr[0] * Qi[j]));
-        s = fma(Pr[3], Ji[j], s);
-        s = fma(Pr[4], Ji[3 + j], s);
-        s = fma(Pr[5], Ji[6 + j], s);
+        rec[L::cvp(i, j) * RS] = QFMA(Pr[2], Ji[6 + j], QFMA(Pr[1], Ji[3 + j], Pr[0] * Ji[j]));
+        double s = QFMA(Pr[2], Qi[6 + j], QFMA(Pr[1], Qi[3 + j], Pr[0] * Qi[j]));
+        s = QFMA(Pr[3], Ji[j], s);
+        s = QFMA(Pr[4], Ji[3 + j], s);
+        s = QFMA(Pr[5], Ji[6 + j], s);
         rec[L::cvp(i, 3 + j) * RS] = s;
       }
     }
@@ -260,25 +261,7 @@ __global__ void __launch_bounds__(32) k_backward_g4(const __grid_constant__ Devi
   }
 
   if (!valid || c != 0) return;
-  if (!a.solve_mode) {
-    a.terms_out[2 * size_t(b)] = QuTk;
-    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
-    return;
-  }
-  const SolveState &st = a.st;
-  st.qutk[b] = QuTk;
-  st.ktquuk[b] = kTQuuk;
-  st.bwd[b] += 1;
-  const double cost = st.cost[b];
-  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
-  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
-    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
-    st.phase[b] = PHASE_DONE;
-  } else {
-    st.alpha[b] = 1.0;
-    st.ls_iter[b] = 0;
-    st.phase[b] = a.search_phase;
-  }
+  backward_finish(p, a, b, QuTk, kTQuuk);
 }
 
 }  // namespace qilqr

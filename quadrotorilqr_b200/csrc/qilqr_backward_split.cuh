@@ -138,25 +138,7 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
   }
 
   if (!valid || c != 0) return;
-  if (!a.solve_mode) {
-    a.terms_out[2 * size_t(b)] = QuTk;
-    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
-    return;
-  }
-  const SolveState &st = a.st;
-  st.qutk[b] = QuTk;
-  st.ktquuk[b] = kTQuuk;
-  st.bwd[b] += 1;
-  const double cost = st.cost[b];
-  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
-  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
-    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
-    st.phase[b] = PHASE_DONE;
-  } else {
-    st.alpha[b] = 1.0;
-    st.ls_iter[b] = 0;
-    st.phase[b] = a.search_phase;
-  }
+  backward_finish(p, a, b, QuTk, kTQuuk);
 }
 
 }  // namespace qilqr

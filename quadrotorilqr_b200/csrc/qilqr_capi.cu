@@ -56,6 +56,20 @@ struct TimedSpan {
 
 }  // namespace
 
+namespace {
+struct SolveCtx {  // what a solve leaves pending when its tail runs on the device (qilqr_solve_device_begin / _finish)
+  bool pending = false;
+  bool compacted = false, on_hi = false;
+  int B = 0, N = 0, m_tail = 0;
+  Problem pr_big{}, pr{};
+  SolveState st_big{}, st{};
+  qilqr_result_t *d_results = nullptr;
+  int64_t launches0 = 0;
+  std::chrono::steady_clock::time_point t_begin, t_switch;
+};
+
+}  // namespace
+
 struct qilqr_solver {
   DeviceParams p{};
   qilqr_options_t opt{};
@@ -86,13 +100,18 @@ struct qilqr_solver {
 
   // workspace
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
-      hist_d, debug_d, misc, wide_d, rec_d;
+      hist_d, debug_d, misc, wide_d, rec_d, totals_d;
   // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
-  DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map;
+  DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map, tail_lists, rec_tail_d;
   bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
-  bool persistent_tail = false;  // EXPERIMENTAL, QILQR_PERSISTENT_TAIL=1: one kernel for the whole compacted tail
-  int *h_counts = nullptr;  // mapped pinned: [0]=search, [1]=active
+  bool persistent_tail = true;  // QILQR_PERSISTENT_TAIL=0: keep the host-driven loop to the end
+  int persist_threshold = 64;   // ... one kernel finishes the solve once at most this many problems are alive
+  int always_hist_cap = 128;    // per-problem cost history kept on the device even when the caller passes no buffer
+  int *h_counts = nullptr;  // mapped pinned: [0] = alive, [1] = active, [2] = sequence number of the compaction
   int *d_counts = nullptr;
+  long long *h_totals = nullptr;  // pinned: sums over the batch of backward passes and rollouts of the last solve
+  SolveCtx ctx;                   // a solve whose tail is still running on the device (begin / finish API)
+  std::mutex mu;                  // one call at a time per handle (the workspace is shared by every entry point)
 };
 
 namespace {
@@ -226,7 +245,7 @@ inline unsigned blocks_for(int n, int per) { return unsigned((n + per - 1) / per
 // Ordered compaction of `list` (n entries) by phase into two lists; the two lengths land in S->h_counts
 // after the next synchronisation of S->cur.
 void launch_compact(qilqr_solver *S, const int *list, int n, const int *phase, int *out_s, int *out_a,
-                    int phase_s = PHASE_SEARCH, int phase_a = PHASE_ACTIVE) {
+                    int phase_s = kMaskSearch, int phase_a = kMaskActive) {
   const int seq = ++S->seq;
   if (n <= 4096) {
     // a small CTA is enough for the short lists of a solve's tail (and fits next to the bulk kernels' CTAs)
@@ -268,31 +287,43 @@ int wait_counts(qilqr_solver *S, cudaStream_t st) {
   return QILQR_OK;
 }
 
+// Opt-in to more than 48 kB of dynamic shared memory and the maximum shared-memory carve-out.  Function
+// attributes are per device (per context): qilqr_create calls this after cudaSetDevice for every handle.
+size_t riccati_extra_smem() {  // QILQR_RICCATI_EXTRA_SMEM: occupancy experiments only
+  static const size_t extra = std::getenv("QILQR_RICCATI_EXTRA_SMEM") ? std::atoi(std::getenv("QILQR_RICCATI_EXTRA_SMEM")) : 0;
+  return extra;
+}
+template <class K>
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+cudaError_t configure_kernels() {
+  cudaError_t e;
+  if ((e = opt_in_smem(k_backward_g4<1>, sizeof(double) * g4::smem_doubles(1))) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_backward_g4<2>, sizeof(double) * g4::smem_doubles(2))) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_backward_g4<4>, sizeof(double) * g4::smem_doubles(4))) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_riccati_g4<false>, sizeof(double) * g4::split_smem_doubles(false) + riccati_extra_smem())) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_riccati_g4<true>, sizeof(double) * g4::split_smem_doubles(true) + riccati_extra_smem())) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_riccati_dense, sizeof(double) * dn::smem_doubles())) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_tail_persistent<false>, sizeof(double) * tp::smem_doubles(false))) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_tail_persistent<true>, sizeof(double) * tp::smem_doubles(true))) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
 template <int KPP>
 void launch_g4(qilqr_solver *S, const BackwardArgs &ba) {
   const size_t smem = sizeof(double) * g4::smem_doubles(KPP);
-  static std::once_flag configured;  // several solver handles may launch from different host threads
-  std::call_once(configured, [&] {
-    cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    cudaFuncSetAttribute(k_backward_g4<KPP>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                         cudaSharedmemCarveoutMaxShared);
-  });
   k_backward_g4<KPP><<<blocks_for(ba.n, 8), 32, smem, S->cur>>>(S->p, ba);
 }
-// ILQR::backwards_pass for the problems in ba.list: quad kernel when Q has no pose/velocity
-// coupling, one-thread-per-problem kernel otherwise.
+// ILQR::backwards_pass for the problems in ba.list: linearisation kernel + TMA-fed Riccati kernel
 template <bool DENSEQ>
 int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   const int n8 = (ba.n + 7) & ~7;
   const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * g4::rect(DENSEQ);
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
-  static const size_t extra = std::getenv("QILQR_RICCATI_EXTRA_SMEM") ? std::atoi(std::getenv("QILQR_RICCATI_EXTRA_SMEM")) : 0;
-  const size_t smem = sizeof(double) * g4::split_smem_doubles(DENSEQ) + extra;  // `extra`: occupancy experiments only
-  static std::once_flag configured;
-  std::call_once(configured, [&] {
-    cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    cudaFuncSetAttribute(k_riccati_g4<DENSEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  });
+  const size_t smem = sizeof(double) * g4::split_smem_doubles(DENSEQ) + riccati_extra_smem();
   const size_t threads = size_t(n8) * ba.pr.N;
   k_linearise<DENSEQ><<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   k_riccati_g4<DENSEQ><<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
@@ -305,11 +336,6 @@ int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
   const size_t need = sizeof(double) * size_t(n8) * ba.pr.N * dn::DREC;
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
   const size_t smem = sizeof(double) * dn::smem_doubles();
-  static std::once_flag configured;
-  std::call_once(configured, [&] {
-    cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    cudaFuncSetAttribute(k_riccati_dense, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  });
   const size_t threads = size_t(n8) * ba.pr.N;
   k_linearise_dense<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   k_riccati_dense<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
@@ -346,11 +372,28 @@ int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
 
 // ---------------------------------------------------------------------------
 // The batched solve loop (device-resident data).
+//
+// Every problem runs ILQR::solve's own control flow (ilqr.hh:53-87) and counts its own iterations; the host only
+// sequences "super-steps" over lists of problem indices:
+//
+//   backward pass          over the ACTIVE list (problems that need one)        k_linearise + k_riccati_g4
+//   [parallel step sizes]  over the ALIVE list, for the problems in PHASE_WIDE  k_rollout<MODE_WIDE> + k_select_alpha
+//   rollout                over the ALIVE list, for the problems in PHASE_SEARCH k_rollout / k_rollout_ws
+//   compaction             ALIVE list -> next ALIVE and ACTIVE lists (ordered), lengths to the host
+//
+// A problem whose candidate is rejected by the Armijo test stays in PHASE_SEARCH with a smaller step and is simply
+// rolled out again in the next super-step, while the others go on to their next backward pass: a backtracking
+// problem costs only itself a round, there is one host round trip per super-step, and the lists stay sorted (SoA
+// accesses stay coalesced).  Problems never interact, so the results do not depend on this scheduling.
 // ---------------------------------------------------------------------------
+int solve_finish(qilqr_solver *S, SolveCtx &cx);
+
 int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, double *d_traj, double *d_k,
                double *d_K, double *d_hist, int hist_cap, qilqr_result_t *d_results, double *d_debug,
-               int debug_cap) {
+               int debug_cap, bool async_tail = false) {
   if (B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "bad batch/knots/desired_count");
+  SolveCtx &cx = S->ctx;
+  if (cx.pending) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "a solve begun with qilqr_solve_device_begin is still pending");
   QCUDA(S, cudaSetDevice(S->device));
   int rc = ensure_state(S, B);
   if (rc) return rc;
@@ -363,60 +406,66 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
     d_K = S->gK.as<double>();
   }
+  if (!d_hist && S->always_hist_cap > 0) {  // always-on cost history (8 bytes per completed iteration and problem)
+    hist_cap = S->always_hist_cap;
+    QCUDA(S, S->hist_d.ensure(sizeof(double) * size_t(hist_cap) * B));
+    d_hist = S->hist_d.as<double>();
+  }
   cudaStream_t st_ = S->stream;
   S->cur = st_;  // (an earlier solve that failed in its tail may have left the high-priority stream selected)
   S->in_tail = false;
   Problem pr{B, N, Bd, d_traj, S->buf1.as<double>(), d_desired, d_k, d_K};
   SolveState st = make_state(S, B, d_hist, d_hist ? hist_cap : 0);
-  int *listA[2] = {S->lists.as<int>(), S->lists.as<int>() + B};
-  int *listS[2] = {S->lists.as<int>() + 2 * size_t(B), S->lists.as<int>() + 3 * size_t(B)};
+  int *listL[2] = {S->lists.as<int>(), S->lists.as<int>() + B};                      // alive
+  int *listA[2] = {S->lists.as<int>() + 2 * size_t(B), S->lists.as<int>() + 3 * size_t(B)};  // active
 
   S->stats = qilqr_solve_stats_t{};
-  const int64_t launches0 = S->launches;
-  const auto t_begin = std::chrono::steady_clock::now();
-  auto t_switch = t_begin;
+  cx = SolveCtx{};
+  cx.B = B; cx.N = N; cx.d_results = d_results;
+  cx.launches0 = S->launches;
+  cx.t_begin = cx.t_switch = std::chrono::steady_clock::now();
 
-  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B);
+  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B, S->p.max_iters);
   k_cost_trajectory<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, d_traj, d_desired, B, N, Bd, st.cost);
   S->launches += 2;
 
   const bool capture_debug = S->opt.populate_debug && d_debug && debug_cap > 0;
-  int n_active = B;
-  const int *active = nullptr;  // nullptr = identity list
-  int cur = 0;
-  bool on_hi = false;
-  bool compacted = false;  // the remaining problems live in the dense mini-batch (pr / st point there)
-  const Problem pr_big = pr;
-  const SolveState st_big = st;
-  int B_eff = B, m_tail = 0;
   const int P_alpha = S->opt.num_parallel_alphas > 1 ? S->opt.num_parallel_alphas : 1;
-  int *listF = S->lists.as<int>() + 4 * size_t(B);
   if (P_alpha > 1) QCUDA(S, S->wide_d.ensure(sizeof(double) * size_t(P_alpha) * B));
-  for (int i = 0; i < S->opt.max_iters && n_active > 0; ++i) {  // ilqr.hh:58 (max_iters is a double)
-    if (!on_hi && n_active <= S->hi_threshold && B > S->hi_threshold) {
-      // Few problems left: every further iteration is a chain of tiny, latency-bound launches.  Move them
-      // to the high-priority stream so that they are not queued behind another handle's bulk kernels.
+  const bool can_persist = S->persistent_tail && P_alpha <= 1 && !S->generic_path && !S->force_t1 &&
+                           S->split_backward && !capture_debug && !S->profiling;
+  int n_alive = (0.0 < S->opt.max_iters) ? B : 0, n_active = n_alive;
+  const int *alive = nullptr, *active = nullptr;  // nullptr = identity list
+  int cur = 0;
+  cx.pr_big = pr; cx.st_big = st;
+  int B_eff = B;
+  bool persistent_launched = false;
+  for (int epoch = 0; n_alive > 0; ++epoch) {
+    if (!cx.on_hi && n_alive <= S->hi_threshold && B > S->hi_threshold) {
+      // Few problems left: every further super-step is a chain of tiny, latency-bound launches.  Move them
+      // to the high-priority stream so that they are not queued behind another handle's bulk kernels ...
       if (S->tail_stream) {
         cudaEventRecord(S->ev_switch, st_);
         cudaStreamWaitEvent(S->stream_hi, S->ev_switch, 0);
         st_ = S->stream_hi;
         S->cur = st_;
       }
-      on_hi = true;
+      cx.on_hi = true;
       S->in_tail = true;
-      t_switch = std::chrono::steady_clock::now();
-      if (S->tail_compaction && !capture_debug && active) {
+      cx.t_switch = std::chrono::steady_clock::now();
+      if (S->tail_compaction && !capture_debug && alive) {
         // ... and into a dense mini-batch: m problems, pitch m instead of B
-        const int m = n_active;
+        const int m = n_alive;
         const size_t md = size_t(m);
         QCUDA(S, S->tail_traj.ensure(sizeof(double) * 2 * N * 17 * md));
         QCUDA(S, S->tail_gains.ensure(sizeof(double) * N * 52 * md));
         QCUDA(S, S->tail_sd.ensure(sizeof(double) * StateLayout::kDoubles * md));
         QCUDA(S, S->tail_si.ensure(sizeof(int) * StateLayout::kInts * md));
         QCUDA(S, S->tail_map.ensure(sizeof(int) * md));
+        QCUDA(S, S->tail_lists.ensure(sizeof(int) * 4 * md));
         if (Bd != 1) QCUDA(S, S->tail_des.ensure(sizeof(double) * N * 17 * md));
         if (st.cost_hist) QCUDA(S, S->tail_hist.ensure(sizeof(double) * size_t(st.hist_cap) * md));
-        QCUDA(S, cudaMemcpyAsync(S->tail_map.ptr, active, sizeof(int) * md, cudaMemcpyDeviceToDevice, st_));
+        QCUDA(S, cudaMemcpyAsync(S->tail_map.ptr, alive, sizeof(int) * md, cudaMemcpyDeviceToDevice, st_));
         double *tt = S->tail_traj.as<double>(), *tg = S->tail_gains.as<double>();
         double *mini_des = (Bd != 1) ? S->tail_des.as<double>() : nullptr;
         Problem pm{m, N, Bd != 1 ? m : 1, tt, tt + size_t(N) * 17 * md, mini_des ? mini_des : d_desired, tg,
@@ -424,117 +473,108 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         SolveState sm = make_state_from(S->tail_sd.as<double>(), S->tail_si.as<int>(), m,
                                         st.cost_hist ? S->tail_hist.as<double>() : nullptr, st.hist_cap);
         dim3 grid(blocks_for(m, 128), 32);
-        k_tail_gather<<<grid, 128, 0, st_>>>(pr_big, st_big, pm, sm, mini_des, S->tail_map.as<int>(), m);
+        k_tail_gather<<<grid, 128, 0, st_>>>(cx.pr_big, cx.st_big, pm, sm, mini_des, S->tail_map.as<int>(), m);
         ++S->launches;
         pr = pm;
         st = sm;
-        active = nullptr;  // identity list over the mini-batch
         B_eff = m;
-        m_tail = m;
-        compacted = true;
-        if (S->persistent_tail && P_alpha <= 1 && !S->generic_path && !S->force_t1 && S->split_backward) {
-          // the rest of the solve for these m problems in one launch (qilqr_tail_persistent.cuh)
-          const int tiles = (m + 7) / 8;
-          const bool dq = !S->q_block_diagonal;
-          if (S->rec_d.ensure(sizeof(double) * size_t(tiles) * 8 * N * g4::rect(dq)) != cudaSuccess)
-            return fail(S, QILQR_ERR_OUT_OF_MEMORY, "out of device memory for the linearisation records");
-          const size_t smem = sizeof(double) * tp::smem_doubles(dq);
-          if (dq) k_tail_persistent<true><<<tiles, 96, smem, st_>>>(S->p, pm, sm, S->rec_d.as<double>(), m, i);
-          else k_tail_persistent<false><<<tiles, 96, smem, st_>>>(S->p, pm, sm, S->rec_d.as<double>(), m, i);
-          ++S->launches;
-          break;
-        }
+        cx.m_tail = m;
+        cx.compacted = true;
+        // the lists of the mini-batch: everything is alive, the active ones need a compaction
+        int *tl = S->tail_lists.as<int>();
+        listL[0] = tl; listL[1] = tl + md; listA[0] = tl + 2 * md; listA[1] = tl + 3 * md;
+        cur = 0;
+        launch_compact(S, nullptr, m, st.phase, listL[1], listA[0], kMaskAlive, kMaskActive);
+        if ((rc = wait_counts(S, st_))) return rc;
+        alive = nullptr;
+        active = listA[0];
+        n_active = S->h_counts[1];
       }
     }
-    const bool wide = P_alpha > 1 && i > 0;  // iteration 0 is an unconditional full step (ilqr.hh:70-73)
-    BackwardArgs ba{pr, st, active, n_active, i, wide ? PHASE_WIDE : PHASE_SEARCH, 1, nullptr, nullptr};
-    {
-      SpanGuard g(S, 0);
-      if ((rc = launch_backward(S, ba))) return rc;
+    if (can_persist && n_alive <= S->persist_threshold) {
+      // the rest of the solve for these problems in one launch (qilqr_tail_persistent.cuh); the host is done
+      const int tiles = (n_alive + 7) / 8;
+      const bool dq = !S->q_block_diagonal;
+      if (S->rec_tail_d.ensure(sizeof(double) * size_t(tiles) * 8 * N * g4::rect(dq)) != cudaSuccess)
+        return fail(S, QILQR_ERR_OUT_OF_MEMORY, "out of device memory for the linearisation records");
+      const size_t smem = sizeof(double) * tp::smem_doubles(dq);
+      if (dq) k_tail_persistent<true><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), alive, n_alive, epoch);
+      else k_tail_persistent<false><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), alive, n_alive, epoch);
+      ++S->launches;
+      persistent_launched = true;
+      break;
     }
-    S->stats.backward_problem_knots += int64_t(n_active) * N;
-    S->stats.problem_iterations += n_active;
-    ++S->launches;
-    int n_next = 0;
-    // forward_sim + cost + Armijo/convergence bookkeeping for the problems of `list` at their alpha[b]
-    auto rollout_list = [&](const int *list, int n) {
-      RolloutArgs ra{pr, st, list, n, i, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1};
+    if (n_active > 0) {
+      BackwardArgs ba{pr, st, active, n_active, epoch, P_alpha > 1 ? 1 : 0, 1, nullptr, nullptr};
+      {
+        SpanGuard g(S, 0);
+        if ((rc = launch_backward(S, ba))) return rc;
+      }
+      S->stats.backward_problem_knots += int64_t(n_active) * N;
+      ++S->launches;
+    }
+    if (P_alpha > 1 && epoch > 0) {
+      // parallel line search: P_alpha step sizes per problem as independent cost-only rollouts, then the first
+      // (largest) one that passes the Armijo test -- what the sequential search would accept
+      RolloutArgs rw{pr, st, alive, n_alive, epoch, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha, 1};
       {
         SpanGuard g(S, 1);
-        launch_rollout(S, ra, n, st_);
+        launch_rollout(S, rw, n_alive * P_alpha, st_);
       }
-      S->stats.rollout_problem_knots += int64_t(n) * N;
-      S->stats.problem_rollouts += n;
+      k_select_alpha<<<blocks_for(n_alive, 128), 128, 0, st_>>>(S->p, st, alive, n_alive, B_eff, S->wide_d.as<double>(), P_alpha);
+      S->launches += 2;
+    }
+    {
+      // forward_sim + cost + Armijo / convergence bookkeeping for every problem that is searching at its alpha[b]
+      RolloutArgs ra{pr, st, alive, n_alive, epoch, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1, 1};
+      {
+        SpanGuard g(S, 1);
+        launch_rollout(S, ra, n_alive, st_);
+      }
       ++S->launches;
       if (capture_debug) {
-        dim3 grid(blocks_for(n, 128), 32);
-        k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, list, n, i, d_debug, debug_cap);
+        dim3 grid(blocks_for(n_alive, 128), 32);
+        k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, alive, n_alive, epoch, d_debug, debug_cap);
         ++S->launches;
       }
-    };
-    if (!wide) {
-      launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
-      if ((rc = wait_counts(S, st_))) return rc;
-      int n_search = S->h_counts[0];
-      int s = 0, rounds = 0;
-      while (n_search > 0) {  // sequential backtracking: one more rollout for every problem that was rejected
-        rollout_list(listS[s], n_search);
-        launch_compact(S, listS[s], n_search, st.phase, listS[1 - s], listA[1 - cur]);
-        if ((rc = wait_counts(S, st_))) return rc;
-        n_search = S->h_counts[0];
-        n_next = S->h_counts[1];
-        s = 1 - s;
-        ++rounds;
-      }
-      if (rounds > 1) {  // rebuild the ordered active list from this iteration's list
-        launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
-        if ((rc = wait_counts(S, st_))) return rc;
-        n_next = S->h_counts[1];
-      }
-    } else {
-      // parallel line search: P_alpha step sizes per problem and round as independent cost-only rollouts
-      launch_compact(S, active, n_active, st.phase, listS[0], listF, PHASE_WIDE, PHASE_SEARCH);
-      if ((rc = wait_counts(S, st_))) return rc;
-      int n_wide = S->h_counts[0];
-      int s = 0;
-      while (n_wide > 0) {
-        RolloutArgs rw{pr, st, listS[s], n_wide, i, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha};
-        {
-          SpanGuard g(S, 1);
-          launch_rollout(S, rw, n_wide * P_alpha, st_);
-        }
-        S->stats.rollout_problem_knots += int64_t(n_wide) * P_alpha * N;
-        k_select_alpha<<<blocks_for(n_wide, 128), 128, 0, st_>>>(S->p, st, listS[s], n_wide, B_eff, S->wide_d.as<double>(), P_alpha);
-        launch_compact(S, listS[s], n_wide, st.phase, listS[1 - s], listF, PHASE_WIDE, PHASE_SEARCH);
-        S->launches += 2;
-        if ((rc = wait_counts(S, st_))) return rc;
-        n_wide = S->h_counts[0];
-        const int n_found = S->h_counts[1];
-        if (n_found > 0) rollout_list(listF, n_found);  // writes the accepted trajectory (same cost, accepted)
-        s = 1 - s;
-      }
-      launch_compact(S, active, n_active, st.phase, listS[0], listA[1 - cur]);
-      if ((rc = wait_counts(S, st_))) return rc;
-      n_next = S->h_counts[1];
     }
+    launch_compact(S, alive, n_alive, st.phase, listL[1 - cur], listA[1 - cur], kMaskAlive, kMaskActive);
+    if ((rc = wait_counts(S, st_))) return rc;
     drain_spans(S);
     ++S->stats.solver_iterations;
     cur = 1 - cur;
+    alive = listL[cur];
     active = listA[cur];
-    n_active = n_next;
+    n_alive = S->h_counts[0];
+    n_active = S->h_counts[1];
   }
-  if (compacted) {
-    dim3 grid(blocks_for(m_tail, 128), 32);
-    k_tail_scatter<<<grid, 128, 0, st_>>>(pr_big, st_big, pr, st, S->tail_map.as<int>(), m_tail);
+  cx.pr = pr; cx.st = st;
+  cx.pending = true;
+  if (async_tail && persistent_launched) return QILQR_OK;  // qilqr_solve_device_finish completes it
+  return solve_finish(S, cx);
+}
+
+// Scatter the tail's results back, write the result records, rejoin the main stream and wait.
+int solve_finish(qilqr_solver *S, SolveCtx &cx) {
+  if (!cx.pending) return QILQR_OK;
+  cx.pending = false;
+  QCUDA(S, cudaSetDevice(S->device));
+  cudaStream_t st_ = S->cur;
+  const int B = cx.B;
+  if (cx.compacted) {
+    dim3 grid(blocks_for(cx.m_tail, 128), 32);
+    k_tail_scatter<<<grid, 128, 0, st_>>>(cx.pr_big, cx.st_big, cx.pr, cx.st, S->tail_map.as<int>(), cx.m_tail);
     ++S->launches;
   }
-  k_finalize<<<blocks_for(B, 256), 256, 0, st_>>>(st_big, B, d_results);
+  cudaMemsetAsync(S->totals_d.ptr, 0, 2 * sizeof(long long), st_);
+  k_finalize<<<blocks_for(B, 256), 256, 0, st_>>>(cx.st_big, B, cx.d_results, S->totals_d.as<unsigned long long>());
+  cudaMemcpyAsync(S->h_totals, S->totals_d.ptr, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st_);
   {
     dim3 grid(blocks_for(B, 128), 64);
-    k_collect<<<grid, 128, 0, st_>>>(pr_big, st_big.sel);
+    k_collect<<<grid, 128, 0, st_>>>(cx.pr_big, cx.st_big.sel);
   }
   S->launches += 2;
-  if (on_hi && S->tail_stream) {  // rejoin the solver's main stream
+  if (cx.on_hi && S->tail_stream) {  // rejoin the solver's main stream
     cudaEventRecord(S->ev_switch, st_);
     cudaStreamWaitEvent(S->stream, S->ev_switch, 0);
     S->cur = S->stream;
@@ -542,12 +582,15 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   S->in_tail = false;
   QCUDA(S, cudaStreamSynchronize(S->stream));
   QCUDA(S, cudaGetLastError());
-  S->stats.kernel_launches = S->launches - launches0;
+  S->stats.problem_iterations = S->h_totals[0];
+  S->stats.problem_rollouts = S->h_totals[1];
+  S->stats.rollout_problem_knots = S->h_totals[1] * int64_t(cx.N);
+  S->stats.kernel_launches = S->launches - cx.launches0;
   {
     const auto t_end = std::chrono::steady_clock::now();
-    if (!on_hi) t_switch = t_end;
-    S->stats.bulk_wall_ms = std::chrono::duration<double, std::milli>(t_switch - t_begin).count();
-    S->stats.tail_wall_ms = std::chrono::duration<double, std::milli>(t_end - t_switch).count();
+    if (!cx.on_hi) cx.t_switch = t_end;
+    S->stats.bulk_wall_ms = std::chrono::duration<double, std::milli>(cx.t_switch - cx.t_begin).count();
+    S->stats.tail_wall_ms = std::chrono::duration<double, std::milli>(t_end - cx.t_switch).count();
   }
   return QILQR_OK;
 }
@@ -608,6 +651,17 @@ const char *qilqr_error_string(int err) {
   }
 }
 
+const char *qilqr_build_info(void) {
+#if defined(QILQR_STRICT) && defined(QILQR_PORTABLE_LIBM)
+  return "strict+portable-libm: no fused multiply-adds, true divisions, sin/cos/atan2 from qilqr_portable_libm.h "
+         "(-DQILQR_STRICT -DQILQR_PORTABLE_LIBM -fmad=false)";
+#elif defined(QILQR_STRICT)
+  return "strict: no fused multiply-adds, true divisions (-DQILQR_STRICT -fmad=false)";
+#else
+  return "production: explicit fused multiply-adds, reciprocal multiplies (-fmad=false)";
+#endif
+}
+
 int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, double dt_s,
                  const qilqr_options_t *options, int device, qilqr_solver_t **out) {
   if (!model || !Q || !R || !options || !out) return QILQR_ERR_INVALID_ARGUMENT;
@@ -652,6 +706,8 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   if (const char *e = std::getenv("QILQR_ROLLOUT")) S->rollout_ws = std::string(e) != "thread";
   if (const char *e = std::getenv("QILQR_TAIL_COMPACTION")) S->tail_compaction = std::atoi(e) != 0;
   if (const char *e = std::getenv("QILQR_PERSISTENT_TAIL")) S->persistent_tail = std::atoi(e) != 0;
+  if (const char *e = std::getenv("QILQR_PERSIST_THRESHOLD")) S->persist_threshold = std::atoi(e);
+  if (const char *e = std::getenv("QILQR_ALWAYS_HIST_CAP")) S->always_hist_cap = std::max(0, std::atoi(e));
   if (const char *e = std::getenv("QILQR_WS_THRESHOLD")) S->ws_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);
@@ -668,10 +724,13 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
       cudaStreamCreateWithPriority(&S->stream_hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaEventCreateWithFlags(&S->ev_switch, cudaEventDisableTiming) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void **>(&S->h_counts), 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer(reinterpret_cast<void **>(&S->d_counts), S->h_counts, 0) != cudaSuccess) {
-    delete S;
+      cudaHostGetDevicePointer(reinterpret_cast<void **>(&S->d_counts), S->h_counts, 0) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void **>(&S->h_totals), 2 * sizeof(long long), cudaHostAllocDefault) != cudaSuccess ||
+      S->totals_d.ensure(2 * sizeof(long long)) != cudaSuccess || configure_kernels() != cudaSuccess) {
+    qilqr_destroy(S);
     return QILQR_ERR_CUDA;
   }
+  S->h_totals[0] = S->h_totals[1] = 0;
   S->cur = S->stream;
   std::memset(S->h_counts, 0, 4 * sizeof(int));
   *out = S;
@@ -681,14 +740,17 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
 void qilqr_destroy(qilqr_solver_t *S) {
   if (!S) return;
   cudaSetDevice(S->device);
-  cudaStreamSynchronize(S->stream);
+  if (S->stream) cudaStreamSynchronize(S->stream);
+  if (S->stream_hi) cudaStreamSynchronize(S->stream_hi);
   for (DeviceBuffer *b : {&S->buf1, &S->gk, &S->gK, &S->state_d, &S->state_i, &S->lists, &S->desired_soa,
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
-                          &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->tail_traj, &S->tail_gains, &S->tail_des,
-                          &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map})
+                          &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->totals_d, &S->tail_traj, &S->tail_gains,
+                          &S->tail_des, &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map, &S->tail_lists,
+                          &S->rec_tail_d})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
+  if (S->h_totals) cudaFreeHost(S->h_totals);
   if (S->ev_switch) cudaEventDestroy(S->ev_switch);
   if (S->stream_hi) cudaStreamDestroy(S->stream_hi);
   if (S->stream) cudaStreamDestroy(S->stream);
@@ -1003,7 +1065,7 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
   Problem pr{B, N, Bd, S->traj_soa.as<double>(), S->buf1.as<double>(), S->desired_soa.as<double>(),
              S->gk.as<double>(), S->gK.as<double>()};
   SolveState st = make_state(S, B, nullptr, 0);
-  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B);
+  k_init_state<<<blocks_for(B, 256), 256, 0, st_>>>(st, B, 1.0);
   ++S->launches;
   std::vector<double> q(B), kq(B);
   for (int b = 0; b < B; ++b) { q[b] = terms[2 * b]; kq[b] = terms[2 * b + 1]; }

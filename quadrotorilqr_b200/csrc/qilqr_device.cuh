@@ -17,6 +17,38 @@
 
 #define QD __device__ __forceinline__
 
+// ---------------------------------------------------------------------------
+// Rounding contract.  The library is compiled with -fmad=false: the compiler never contracts a
+// multiply and an add on its own, so the same inline function rounds the same way in every kernel it
+// is inlined into (bulk, tail and API kernels are bit-identical by construction).  Every fused
+// multiply-add is therefore written out:
+//   QFMA(a, b, c)   a*b + c in ONE rounding (production) -- the summation order is the reference's
+//                   (Eigen's coefficient-wise dot products, k ascending), only the rounding is fused;
+//   QDIV(x, d, r)   x / d, computed as x * r with r = 1/d precomputed (production).
+// The opt-in STRICT build (-DQILQR_STRICT, libqilqr_b200_strict.so; tools/full_batch_parity.py) turns
+// both back into what the reference's x86-64 build executes -- a rounded product followed by a rounded
+// sum, and a true division -- which leaves the CUDA math library (sin, cos, atan2 against glibc's) as
+// the only rounding difference to the CPU oracle.
+// ---------------------------------------------------------------------------
+#ifdef QILQR_STRICT
+#define QFMA(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#define QDIV(x, d, r) ((x) / (d))
+#else
+#define QFMA(a, b, c) fma((a), (b), (c))
+#define QDIV(x, d, r) ((x) * (r))
+#endif
+
+// sin / cos / atan2: the CUDA math library, or -- for the bit-for-bit comparison with the oracle only
+// (-DQILQR_PORTABLE_LIBM, see qilqr_portable_libm.h) -- a portable implementation shared with the host
+#ifdef QILQR_PORTABLE_LIBM
+#include "qilqr_portable_libm.h"
+#define QSINCOS(x, s, c) qilqr_plibm::sincos((x), (s), (c))
+#define QATAN2(y, x) qilqr_plibm::atan2((y), (x))
+#else
+#define QSINCOS(x, s, c) sincos((x), (s), (c))
+#define QATAN2(y, x) atan2((y), (x))
+#endif
+
 namespace qilqr {
 
 constexpr double kEps = 1e-14;  // manif Constants<double>::eps
@@ -49,40 +81,40 @@ QD void m3_mul(const double *A, const double *B, double *C) {  // C = A B
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = fma(A[3 * i + 2], B[6 + j], fma(A[3 * i + 1], B[3 + j], A[3 * i] * B[j]));
+      C[3 * i + j] = QFMA(A[3 * i + 2], B[6 + j], QFMA(A[3 * i + 1], B[3 + j], A[3 * i] * B[j]));
 }
 QD void m3_madd(const double *A, const double *B, double *C) {  // C += A B
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = fma(A[3 * i + 2], B[6 + j], fma(A[3 * i + 1], B[3 + j], fma(A[3 * i], B[j], C[3 * i + j])));
+      C[3 * i + j] = QFMA(A[3 * i + 2], B[6 + j], QFMA(A[3 * i + 1], B[3 + j], QFMA(A[3 * i], B[j], C[3 * i + j])));
 }
 QD void m3_mulT(const double *A, const double *B, double *C) {  // C = A^T B
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = fma(A[6 + i], B[6 + j], fma(A[3 + i], B[3 + j], A[i] * B[j]));
+      C[3 * i + j] = QFMA(A[6 + i], B[6 + j], QFMA(A[3 + i], B[3 + j], A[i] * B[j]));
 }
 QD void m3_maddT(const double *A, const double *B, double *C) {  // C += A^T B
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = fma(A[6 + i], B[6 + j], fma(A[3 + i], B[3 + j], fma(A[i], B[j], C[3 * i + j])));
+      C[3 * i + j] = QFMA(A[6 + i], B[6 + j], QFMA(A[3 + i], B[3 + j], QFMA(A[i], B[j], C[3 * i + j])));
 }
 QD void m3_vec(const double *A, const double *v, double *r) {  // r = A v
 #pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = fma(A[3 * i + 2], v[2], fma(A[3 * i + 1], v[1], A[3 * i] * v[0]));
+  for (int i = 0; i < 3; ++i) r[i] = QFMA(A[3 * i + 2], v[2], QFMA(A[3 * i + 1], v[1], A[3 * i] * v[0]));
 }
 QD void m3T_vec(const double *A, const double *v, double *r) {  // r = A^T v
 #pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = fma(A[6 + i], v[2], fma(A[3 + i], v[1], A[i] * v[0]));
+  for (int i = 0; i < 3; ++i) r[i] = QFMA(A[6 + i], v[2], QFMA(A[3 + i], v[1], A[i] * v[0]));
 }
 QD void m3T_vec_add(const double *A, const double *v, double *r) {  // r += A^T v
 #pragma unroll
-  for (int i = 0; i < 3; ++i) r[i] = fma(A[6 + i], v[2], fma(A[3 + i], v[1], fma(A[i], v[0], r[i])));
+  for (int i = 0; i < 3; ++i) r[i] = QFMA(A[6 + i], v[2], QFMA(A[3 + i], v[1], QFMA(A[i], v[0], r[i])));
 }
 QD void m3_transpose(const double *A, double *T) {
 #pragma unroll
@@ -94,18 +126,18 @@ QD void m3_transpose(const double *A, double *T) {
 QD void m3_mul_hat(const double *M, const double *w, double *C) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    C[3 * i + 0] = fma(M[3 * i + 1], w[2], -(M[3 * i + 2] * w[1]));
-    C[3 * i + 1] = fma(M[3 * i + 2], w[0], -(M[3 * i + 0] * w[2]));
-    C[3 * i + 2] = fma(M[3 * i + 0], w[1], -(M[3 * i + 1] * w[0]));
+    C[3 * i + 0] = QFMA(M[3 * i + 1], w[2], -(M[3 * i + 2] * w[1]));
+    C[3 * i + 1] = QFMA(M[3 * i + 2], w[0], -(M[3 * i + 0] * w[2]));
+    C[3 * i + 2] = QFMA(M[3 * i + 0], w[1], -(M[3 * i + 1] * w[0]));
   }
 }
 // C = hat(t) * M  (row i of hat(t) has two non-zeros)
 QD void m3_hat_mul(const double *t, const double *M, double *C) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    C[0 + j] = fma(t[1], M[6 + j], -(t[2] * M[3 + j]));
-    C[3 + j] = fma(t[2], M[0 + j], -(t[0] * M[6 + j]));
-    C[6 + j] = fma(t[0], M[3 + j], -(t[1] * M[0 + j]));
+    C[0 + j] = QFMA(t[1], M[6 + j], -(t[2] * M[3 + j]));
+    C[3 + j] = QFMA(t[2], M[0 + j], -(t[0] * M[6 + j]));
+    C[6 + j] = QFMA(t[0], M[3 + j], -(t[1] * M[0 + j]));
   }
 }
 
@@ -132,7 +164,7 @@ QD void quat_compose(const double *a, const double *b, double *r) {
   double y = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 1), QM(1, 3)), QM(2, 0)), -QM(0, 2));
   double z = __dadd_rn(__dadd_rn(__dadd_rn(QM(3, 2), QM(2, 3)), QM(0, 1)), -QM(1, 0));
 #undef QM
-  const double sq = x * x + y * y + z * z + w * w;
+  const double sq = QFMA(w, w, QFMA(z, z, QFMA(y, y, x * x)));
   if (fabs(sq - 1.0) > kEps) {
     const double s = 2.0 / (1.0 + sq);
     x *= s; y *= s; z *= s; w *= s;
@@ -156,9 +188,9 @@ QD void hat_sq(const double *w, double *WW) {  // hat(w)^2, exactly as the matri
 QD void so3_jac_from_coeffs(const double *w, double a, double b, double *J) {
   double WW[9];
   hat_sq(w, WW);
-  J[0] = fma(b, WW[0], 1.0);          J[1] = fma(b, WW[1], -a * w[2]); J[2] = fma(b, WW[2], a * w[1]);
-  J[3] = fma(b, WW[3], a * w[2]);     J[4] = fma(b, WW[4], 1.0);       J[5] = fma(b, WW[5], -a * w[0]);
-  J[6] = fma(b, WW[6], -a * w[1]);    J[7] = fma(b, WW[7], a * w[0]);  J[8] = fma(b, WW[8], 1.0);
+  J[0] = QFMA(b, WW[0], 1.0);          J[1] = QFMA(b, WW[1], -a * w[2]); J[2] = QFMA(b, WW[2], a * w[1]);
+  J[3] = QFMA(b, WW[3], a * w[2]);     J[4] = QFMA(b, WW[4], 1.0);       J[5] = QFMA(b, WW[5], -a * w[0]);
+  J[6] = QFMA(b, WW[6], -a * w[1]);    J[7] = QFMA(b, WW[7], a * w[0]);  J[8] = QFMA(b, WW[8], 1.0);
 }
 // theta^2, theta, sin(theta), cos(theta) of a rotation vector, evaluated once and shared by the
 // Jacobians that manif evaluates separately (ljac/ljacinv/fillQ all use the same theta).
@@ -167,11 +199,11 @@ struct Angle {
 };
 QD Angle angle_of(const double *w) {
   Angle a;
-  a.th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  a.th2 = QFMA(w[2], w[2], QFMA(w[1], w[1], w[0] * w[0]));
   a.th = 0.0; a.s = 0.0; a.c = 1.0;
   if (a.th2 > kEps) {
     a.th = sqrt(a.th2);
-    sincos(a.th, &a.s, &a.c);
+    QSINCOS(a.th, &a.s, &a.c);
   }
   return a;
 }
@@ -189,11 +221,11 @@ QD void so3_ljacinv(const double *w, const Angle &a, double *J) {
 QD void so3_ljacinv(const double *w, double *J) { so3_ljacinv(w, angle_of(w), J); }
 // manif SO3Tangent::exp
 QD void so3_exp(const double *w, double *q) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th2 = QFMA(w[2], w[2], QFMA(w[1], w[1], w[0] * w[0]));
   if (th2 > kEps) {
     const double th = sqrt(th2);
     double s, c;
-    sincos(0.5 * th, &s, &c);
+    QSINCOS(0.5 * th, &s, &c);
     q[0] = s * (w[0] / th); q[1] = s * (w[1] / th); q[2] = s * (w[2] / th); q[3] = c;
   } else {
     q[0] = w[0] / 2.0; q[1] = w[1] / 2.0; q[2] = w[2] / 2.0; q[3] = 1.0;
@@ -201,11 +233,11 @@ QD void so3_exp(const double *w, double *q) {
 }
 // manif SO3::log
 QD void so3_log(const double *q, double *w) {
-  const double s2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  const double s2 = QFMA(q[2], q[2], QFMA(q[1], q[1], q[0] * q[0]));
   double coeff;
   if (s2 > kEps) {
     const double s = sqrt(s2);
-    const double two_angle = 2.0 * ((q[3] < 0.0) ? atan2(-s, -q[3]) : atan2(s, q[3]));
+    const double two_angle = 2.0 * ((q[3] < 0.0) ? QATAN2(-s, -q[3]) : QATAN2(s, q[3]));
     coeff = two_angle / s;
   } else {
     coeff = 2.0;
@@ -230,9 +262,9 @@ QD void se3_fillQ(const double *v, const double *w, const Angle &a, double *Q) {
   }
   // VW = hat(v) hat(w) = w v^T - (v.w) I  (entry by entry, as the matrix product gives it)
   double VW[9], WV[9], WVW[9], VWW[9], WVWW[9];
-  VW[0] = -(v[2] * w[2]) - v[1] * w[1]; VW[1] = v[1] * w[0];                 VW[2] = v[2] * w[0];
-  VW[3] = v[0] * w[1];                 VW[4] = -(v[2] * w[2]) - v[0] * w[0]; VW[5] = v[2] * w[1];
-  VW[6] = v[0] * w[2];                 VW[7] = v[1] * w[2];                 VW[8] = -(v[1] * w[1]) - v[0] * w[0];
+  VW[0] = QFMA(-v[1], w[1], -(v[2] * w[2])); VW[1] = v[1] * w[0];                      VW[2] = v[2] * w[0];
+  VW[3] = v[0] * w[1];                      VW[4] = QFMA(-v[0], w[0], -(v[2] * w[2])); VW[5] = v[2] * w[1];
+  VW[6] = v[0] * w[2];                      VW[7] = v[1] * w[2];                      VW[8] = QFMA(-v[0], w[0], -(v[1] * w[1]));
   m3_transpose(VW, WV);
   m3_mul_hat(WV, w, WVW);
   m3_mul_hat(VW, w, VWW);
@@ -243,11 +275,11 @@ QD void se3_fillQ(const double *v, const double *w, const Angle &a, double *Q) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int ij = 3 * i + j, ji = 3 * j + i;
+      // ((A V + B (..)) - C (..)) - D (..), each product fused into the running sum
       const double t1 = 0.5 * V[ij];
-      const double t2 = B * ((WV[ij] + VW[ij]) + WVW[ij]);
-      const double t3 = C * ((VWW[ij] - VWW[ji]) - 3.0 * WVW[ij]);
-      const double t4 = D * WVWW[ij];
-      Q[ij] = ((t1 + t2) - t3) - t4;
+      const double s2 = (WV[ij] + VW[ij]) + WVW[ij];
+      const double s3 = QFMA(-3.0, WVW[ij], VWW[ij] - VWW[ji]);
+      Q[ij] = QFMA(-D, WVWW[ij], QFMA(-C, s3, QFMA(B, s2, t1)));
     }
 }
 QD void se3_fillQ(const double *v, const double *w, double *Q) { se3_fillQ(v, w, angle_of(w), Q); }
@@ -306,12 +338,12 @@ QD void se3_rjacinv_blocks(const double *tau, const double *Jlinv, const Angle &
 // ---------------------------------------------------------------------------
 // Eigen LLT solve with the precomputed factor: L L^T x = b
 QD void inertia_solve(const DeviceParams &p, const double *b, double *x) {
-  const double y0 = b[0] * p.Linv[0];
-  const double y1 = (b[1] - p.L[3] * y0) * p.Linv[1];
-  const double y2 = (b[2] - p.L[6] * y0 - p.L[7] * y1) * p.Linv[2];
-  x[2] = y2 * p.Linv[2];
-  x[1] = (y1 - p.L[7] * x[2]) * p.Linv[1];
-  x[0] = (y0 - p.L[3] * x[1] - p.L[6] * x[2]) * p.Linv[0];
+  const double y0 = QDIV(b[0], p.L[0], p.Linv[0]);
+  const double y1 = QDIV(QFMA(-p.L[3], y0, b[1]), p.L[4], p.Linv[1]);
+  const double y2 = QDIV(QFMA(-p.L[7], y1, QFMA(-p.L[6], y0, b[2])), p.L[8], p.Linv[2]);
+  x[2] = QDIV(y2, p.L[8], p.Linv[2]);
+  x[1] = QDIV(QFMA(-p.L[7], x[2], y1), p.L[4], p.Linv[1]);
+  x[0] = QDIV(QFMA(-p.L[6], x[2], QFMA(-p.L[3], x[1], y0)), p.L[0], p.Linv[0]);
 }
 
 // Body acceleration of continuous_dynamics (quadrotor_model.cc:65-78): acc[6]
@@ -320,17 +352,18 @@ QD void body_acceleration(const DeviceParams &p, const double *R /*rotation of q
   const double usum = ((u[0] + u[1]) + u[2]) + u[3];
   acc[0] = -p.g * R[6];
   acc[1] = -p.g * R[7];
-  acc[2] = -p.g * R[8] + usum / p.mass;
+  acc[2] = QFMA(-p.g, R[8], usum / p.mass);
   double M[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    M[i] = fma(p.moment_arms[4 * i + 3], u[3],
-               fma(p.moment_arms[4 * i + 2], u[2], fma(p.moment_arms[4 * i + 1], u[1], p.moment_arms[4 * i] * u[0])));
+    M[i] = QFMA(p.moment_arms[4 * i + 3], u[3],
+               QFMA(p.moment_arms[4 * i + 2], u[2], QFMA(p.moment_arms[4 * i + 1], u[1], p.moment_arms[4 * i] * u[0])));
   const double *om = vel + 3;
-  double Iw[3];
-  m3_vec(p.inertia, om, Iw);
-  const double rhs[3] = {M[0] - (om[1] * Iw[2] - om[2] * Iw[1]), M[1] - (om[2] * Iw[0] - om[0] * Iw[2]),
-                         M[2] - (om[0] * Iw[1] - om[1] * Iw[0])};
+  // M - (hat(omega) * inertia) * omega, in the reference's association (quadrotor_model.cc:76-77)
+  double HI[9], HIw[3];
+  m3_hat_mul(om, p.inertia, HI);
+  m3_vec(HI, om, HIw);
+  const double rhs[3] = {M[0] - HIw[0], M[1] - HIw[1], M[2] - HIw[2]};
   inertia_solve(p, rhs, acc + 3);
 }
 
@@ -357,7 +390,7 @@ QD void discrete_step(const DeviceParams &p, double *t, double *q, double *vel, 
 #pragma unroll
   for (int i = 0; i < 4; ++i) q[i] = qn[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) vel[i] = vel[i] + p.dt * acc[i];
+  for (int i = 0; i < 6; ++i) vel[i] = QFMA(p.dt, acc[i], vel[i]);
 }
 
 // The non-trivial 3x3 blocks of A = d(discrete_dynamics)/dx at (x, u)
@@ -435,7 +468,7 @@ QD void dynamics_blocks(const DeviceParams &p, const double *q, const double *ve
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) A.Wd[3 * i + j] = ((i == j) ? 1.0 : 0.0) + p.dt * Wc[3 * i + j];
+    for (int j = 0; j < 3; ++j) A.Wd[3 * i + j] = QFMA(p.dt, Wc[3 * i + j], (i == j) ? 1.0 : 0.0);
 }
 
 // ---------------------------------------------------------------------------
@@ -455,8 +488,8 @@ QD double quadratic_cost_state(const DeviceParams &p, const double *dx) {
   for (int j = 0; j < 12; ++j) {
     double y = dx[0] * p.Q[j];
 #pragma unroll
-    for (int i = 1; i < 12; ++i) y = fma(dx[i], p.Q[12 * i + j], y);
-    cx = (j == 0) ? y * dx[0] : fma(y, dx[j], cx);
+    for (int i = 1; i < 12; ++i) y = QFMA(dx[i], p.Q[12 * i + j], y);
+    cx = (j == 0) ? y * dx[0] : QFMA(y, dx[j], cx);
   }
   return cx;
 }
@@ -466,8 +499,8 @@ QD double quadratic_cost_control(const DeviceParams &p, const double *du) {
   for (int j = 0; j < 4; ++j) {
     double y = du[0] * p.R[j];
 #pragma unroll
-    for (int i = 1; i < 4; ++i) y = fma(du[i], p.R[4 * i + j], y);
-    cu = (j == 0) ? y * du[0] : fma(y, du[j], cu);
+    for (int i = 1; i < 4; ++i) y = QFMA(du[i], p.R[4 * i + j], y);
+    cu = (j == 0) ? y * du[0] : QFMA(y, du[j], cu);
   }
   return cu;
 }

@@ -74,9 +74,14 @@ QD void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" :
 
 // A global load the compiler may not sink towards its first use (volatile asm keeps program order):
 // lets a kernel issue all the loads of a loop iteration up front, ahead of long dependent arithmetic.
+// NC = true reads through the non-coherent path: only for data that no thread of the running kernel writes (the
+// per-iteration kernels).  The persistent tail kernel rewrites gains and trajectories between its own
+// iterations and must use NC = false.
+template <bool NC = true>
 QD double ldg_early(const double *ptr) {
   double v;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  if (NC) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  else asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(ptr) : "memory");
   return v;
 }
 
@@ -118,7 +123,9 @@ struct RolloutArgs {
   SolveState st;
   const int *list;  // problems to roll out (nullptr: 0..n-1)
   int n;
-  int iter;  // outer iteration index i of solve()
+  int iter;  // MODE_SOLVE: the solver's super-step number (marks which problems were accepted in this launch; a
+             // problem's own iteration index i of solve() is its count of backward passes - 1);
+             // MODE_LINE_SEARCH: the iteration index to assume (any value > 0)
   int mode;  // RolloutMode
   // MODE_FORWARD only: explicit buffers and step sizes
   const double *cur;
@@ -126,6 +133,8 @@ struct RolloutArgs {
   const double *alpha_in;
   double *cost_out;  // may be nullptr (MODE_WIDE: [palpha][B])
   int palpha;        // MODE_WIDE: step sizes evaluated per problem
+  int check_phase;   // MODE_SOLVE / MODE_WIDE: `list` is the list of ALIVE problems; skip those that are not in
+                     // PHASE_SEARCH / PHASE_WIDE
 };
 
 // line_search() / solve() bookkeeping after one candidate rollout of problem b (ilqr.hh:70-84, 182-193)
@@ -135,8 +144,11 @@ QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, doubl
   st.rollouts[b] += 1;
   st.new_cost[b] = cost;
   const double cur_cost = st.cost[b];
+  // i of solve()'s loop (ilqr.hh:58) for this problem: every problem counts its own iterations, so that problems of
+  // one batch may be at different iterations (a rejected candidate costs only that problem a round)
+  const int it = (a.mode == MODE_SOLVE) ? st.bwd[b] - 1 : a.iter;
   bool accept;
-  if (a.mode == MODE_SOLVE && a.iter == 0) {
+  if (a.mode == MODE_SOLVE && it == 0) {
     accept = true;  // ilqr.hh:70-73: no acceptance test on the first iteration
   } else {
     const double desired = p.desired_reduction_frac * (alpha * st.qutk[b] + alpha * alpha * st.ktquuk[b] / 2.0);
@@ -149,13 +161,15 @@ QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, doubl
     const int nd = st.ndebug[b];
     if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
     st.ndebug[b] = nd + 1;
-    if (a.mode == MODE_SOLVE && a.iter > 0 && is_converged(p, cur_cost, cost)) {
+    if (a.mode == MODE_SOLVE && it > 0 && is_converged(p, cur_cost, cost)) {
       st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
       st.phase[b] = PHASE_DONE;
     } else if (a.mode == MODE_LINE_SEARCH) {
       st.phase[b] = PHASE_DONE;
     } else {
-      st.phase[b] = PHASE_ACTIVE;
+      // the loop bound of ilqr.hh:58, `i < max_iters` with max_iters a double, for the next i = it + 1
+      // (k_finalize turns "done without a status" into QILQR_STATUS_MAX_ITERS)
+      st.phase[b] = (double(it + 1) < p.max_iters) ? PHASE_ACTIVE : PHASE_DONE;
     }
   } else {
     st.alpha[b] = alpha * p.step_update;  // ilqr.hh:189
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
   const int t = (a.mode == MODE_WIDE) ? tid % a.n : tid;
   if (tid >= a.n * ((a.mode == MODE_WIDE) ? a.palpha : 1)) return;
   const int b = a.list ? a.list[t] : t;
+  if (a.check_phase && a.st.phase[b] != ((a.mode == MODE_WIDE) ? PHASE_WIDE : PHASE_SEARCH)) return;
   const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
   const int bd = (Bd == 1) ? 0 : b;
   const double *cur;
@@ -221,8 +236,8 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
     for (int j = 0; j < 4; ++j) {
       double Kd = gK[12 * j] * d[0];
 #pragma unroll
-      for (int s = 1; s < 12; ++s) Kd = fma(gK[12 * j + s], d[s], Kd);
-      u[j] = (ubar[j] + alpha * gk[j]) + Kd;
+      for (int s = 1; s < 12; ++s) Kd = QFMA(gK[12 * j + s], d[s], Kd);
+      u[j] = QFMA(alpha, gk[j], ubar[j]) + Kd;
     }
     if (a.mode != MODE_WIDE) store_point(cand, i, B, b, x, u);
     if (want_cost) {
@@ -264,6 +279,7 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
 // The body shared by k_rollout_ws and the persistent tail kernel: every thread of a 96-thread CTA calls it (it
 // contains CTA barriers); `lane` selects the problem slot, `role` the warp's part, `b` the problem (idle slots
 // shadow a valid problem with valid = false: they must reach the barriers and write nothing).
+template <bool NC = true>
 QD void rollout_ws_run(const DeviceParams &p, const RolloutArgs &a, const int lane, const int role, const bool valid,
                        const int b, double (*s_pose)[7][32], double (*s_vel)[32], double (*s_u)[32]) {
   const int B = a.pr.B, N = a.pr.N, Bd = a.pr.Bd;
@@ -296,13 +312,13 @@ QD void rollout_ws_run(const DeviceParams &p, const RolloutArgs &a, const int la
     if (role == 0) {
       double xbar[13], gk[4], gK[48];
 #pragma unroll
-      for (int c = 0; c < 13; ++c) xbar[c] = ldg_early(&cur[row_index(i, c, 17, B, b)]);
+      for (int c = 0; c < 13; ++c) xbar[c] = ldg_early<NC>(&cur[row_index(i, c, 17, B, b)]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ubar[c] = ldg_early(&cur[row_index(i, 13 + c, 17, B, b)]);
+      for (int c = 0; c < 4; ++c) ubar[c] = ldg_early<NC>(&cur[row_index(i, 13 + c, 17, B, b)]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) gk[e] = ldg_early(&a.pr.gk[row_index(i, e, 4, B, b)]);
+      for (int e = 0; e < 4; ++e) gk[e] = ldg_early<NC>(&a.pr.gk[row_index(i, e, 4, B, b)]);
 #pragma unroll
-      for (int e = 0; e < 48; ++e) gK[e] = ldg_early(&a.pr.gK[row_index(i, e, 48, B, b)]);
+      for (int e = 0; e < 48; ++e) gK[e] = ldg_early<NC>(&a.pr.gK[row_index(i, e, 48, B, b)]);
 #pragma unroll
       for (int c = 0; c < 7; ++c) x[c] = s_pose[i & 1][c][lane];
       double d[12];
@@ -311,8 +327,8 @@ QD void rollout_ws_run(const DeviceParams &p, const RolloutArgs &a, const int la
       for (int j = 0; j < 4; ++j) {
         double Kd = gK[12 * j] * d[0];
 #pragma unroll
-        for (int s = 1; s < 12; ++s) Kd = fma(gK[12 * j + s], d[s], Kd);
-        ubar[j] = (ubar[j] + alpha * gk[j]) + Kd;  // from here on: the new control u_i
+        for (int s = 1; s < 12; ++s) Kd = QFMA(gK[12 * j + s], d[s], Kd);
+        ubar[j] = QFMA(alpha, gk[j], ubar[j]) + Kd;  // from here on: the new control u_i
         s_u[j][lane] = ubar[j];
       }
     } else if (role == 1) {
@@ -361,7 +377,7 @@ QD void rollout_ws_run(const DeviceParams &p, const RolloutArgs &a, const int la
       body_acceleration(p, R, x + 7, ubar, acc);
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        x[7 + c] = x[7 + c] + p.dt * acc[c];
+        x[7 + c] = QFMA(p.dt, acc[c], x[7 + c]);
         s_vel[c][lane] = x[7 + c];
       }
     } else if (role == 2) {
@@ -393,9 +409,11 @@ __global__ void __launch_bounds__(96, QILQR_WS_MINB) k_rollout_ws(const __grid_c
   __shared__ double s_pose[2][7][32], s_vel[6][32], s_u[4][32];
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const int t0 = blockIdx.x * 32 + lane;
-  const bool valid = t0 < a.n;
-  const int t = valid ? t0 : a.n - 1;
-  rollout_ws_run(p, a, lane, role, valid, a.list ? a.list[t] : t, s_pose, s_vel, s_u);
+  const int t = t0 < a.n ? t0 : a.n - 1;
+  const int b = a.list ? a.list[t] : t;
+  const bool valid = t0 < a.n && (!a.check_phase || a.st.phase[b] == PHASE_SEARCH);
+  if (!__syncthreads_or(valid)) return;  // nothing to roll out among these 32 problems
+  rollout_ws_run(p, a, lane, role, valid, b, s_pose, s_vel, s_u);
 }
 
 // ---------------------------------------------------------------------------
@@ -411,6 +429,7 @@ struct Ldlt4 {
   double m[16];
   double l10, l20, l21, l30, l31, l32;
   double dinv[4];  // 1/d_i, or 0 where |d_i| <= DBL_MIN (Eigen's pseudo-inverse of D)
+  double d[4];     // the pivots themselves (read by the STRICT build only, which divides)
   bool s01, s02, s03, s12, s13, s23;
 };
 QD void cswap(bool c, double &a, double &b) {
@@ -450,42 +469,47 @@ QD void ldlt4_compute(Ldlt4 &f) {
   const double d0 = a00;
   const double r0 = 1.0 / d0;
   const bool v0 = fabs(d0) > 0.0;
-  const double l10 = v0 ? a10 * r0 : a10, l20 = v0 ? a20 * r0 : a20, l30 = v0 ? a30 * r0 : a30;
+  const double l10 = v0 ? QDIV(a10, d0, r0) : a10, l20 = v0 ? QDIV(a20, d0, r0) : a20, l30 = v0 ? QDIV(a30, d0, r0) : a30;
   double t0 = d0 * l10;
-  const double d1 = a11 - l10 * t0;
-  const double m21 = a21 - l20 * t0, m31 = a31 - l30 * t0;
+  const double d1 = QFMA(-l10, t0, a11);
+  const double m21 = QFMA(-l20, t0, a21), m31 = QFMA(-l30, t0, a31);
   const double r1 = 1.0 / d1;
   const bool v1 = fabs(d1) > 0.0;
-  const double l21 = v1 ? m21 * r1 : m21, l31 = v1 ? m31 * r1 : m31;
+  const double l21 = v1 ? QDIV(m21, d1, r1) : m21, l31 = v1 ? QDIV(m31, d1, r1) : m31;
   t0 = d0 * l20;
   double t1 = d1 * l21;
-  const double d2 = a22 - fma(l21, t1, l20 * t0);
+  const double d2 = a22 - QFMA(l21, t1, l20 * t0);
   t0 = d0 * l30;
   const double t1b = d1 * l31;
-  const double m32 = a32 - fma(l31, t1, l30 * (d0 * l20));
+  const double m32 = a32 - QFMA(l31, t1, l30 * (d0 * l20));
   const double r2 = 1.0 / d2;
   const bool v2 = fabs(d2) > 0.0;
-  const double l32 = v2 ? m32 * r2 : m32;
+  const double l32 = v2 ? QDIV(m32, d2, r2) : m32;
   const double t2 = d2 * l32;
-  const double d3 = a33 - fma(l32, t2, fma(l31, t1b, l30 * t0));
+  const double d3 = a33 - QFMA(l32, t2, QFMA(l31, t1b, l30 * t0));
   f.l10 = l10; f.l20 = l20; f.l21 = l21; f.l30 = l30; f.l31 = l31; f.l32 = l32;
   f.dinv[0] = fabs(d0) > kMin ? r0 : 0.0;
   f.dinv[1] = fabs(d1) > kMin ? r1 : 0.0;
   f.dinv[2] = fabs(d2) > kMin ? r2 : 0.0;
   f.dinv[3] = fabs(d3) > kMin ? 1.0 / d3 : 0.0;
+  f.d[0] = d0; f.d[1] = d1; f.d[2] = d2; f.d[3] = d3;
 }
 QD void ldlt4_solve(const Ldlt4 &f, double *x /*4, in place*/) {
   cswap(f.s01, x[0], x[1]); cswap(f.s02, x[0], x[2]); cswap(f.s03, x[0], x[3]);
   cswap(f.s12, x[1], x[2]); cswap(f.s13, x[1], x[3]);
   cswap(f.s23, x[2], x[3]);
-  x[1] = x[1] - f.l10 * x[0];
-  x[2] = x[2] - f.l20 * x[0] - f.l21 * x[1];
-  x[3] = x[3] - f.l30 * x[0] - f.l31 * x[1] - f.l32 * x[2];
+  x[1] = QFMA(-f.l10, x[0], x[1]);
+  x[2] = QFMA(-f.l21, x[1], QFMA(-f.l20, x[0], x[2]));
+  x[3] = QFMA(-f.l32, x[2], QFMA(-f.l31, x[1], QFMA(-f.l30, x[0], x[3])));
 #pragma unroll
+#ifdef QILQR_STRICT
+  for (int i = 0; i < 4; ++i) x[i] = (f.dinv[i] != 0.0) ? x[i] / f.d[i] : 0.0;
+#else
   for (int i = 0; i < 4; ++i) x[i] = x[i] * f.dinv[i];
-  x[2] = x[2] - f.l32 * x[3];
-  x[1] = x[1] - f.l21 * x[2] - f.l31 * x[3];
-  x[0] = x[0] - f.l10 * x[1] - f.l20 * x[2] - f.l30 * x[3];
+#endif
+  x[2] = QFMA(-f.l32, x[3], x[2]);
+  x[1] = QFMA(-f.l31, x[3], QFMA(-f.l21, x[2], x[1]));
+  x[0] = QFMA(-f.l30, x[3], QFMA(-f.l20, x[2], QFMA(-f.l10, x[1], x[0])));
   cswap(f.s23, x[2], x[3]);
   cswap(f.s13, x[1], x[3]); cswap(f.s12, x[1], x[2]);
   cswap(f.s03, x[0], x[3]); cswap(f.s02, x[0], x[2]); cswap(f.s01, x[0], x[1]);
@@ -503,12 +527,41 @@ struct BackwardArgs {
   SolveState st;
   const int *list;
   int n;
-  int iter;
-  int search_phase;     // PHASE_SEARCH, or PHASE_WIDE when step sizes are evaluated in parallel
+  int iter;             // the solver's super-step number (informational)
+  int wide;             // 1: step sizes are evaluated in parallel (PHASE_WIDE after the first iteration)
   int solve_mode;       // 1: solve() bookkeeping (exit A); 0: plain backwards_pass
   const double *traj;   // solve_mode == 0 only
   double *terms_out;    // solve_mode == 0 only: [B][2]
 };
+
+// What solve() does with the result of backwards_pass for problem b (ilqr.hh:59-68), or the plain output of
+// backwards_pass when !solve_mode.  One copy for every backward kernel.
+QD void backward_finish(const DeviceParams &p, const BackwardArgs &a, int b, double QuTk, double kTQuuk) {
+  if (!a.solve_mode) {
+    a.terms_out[2 * size_t(b)] = QuTk;
+    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
+    return;
+  }
+  const SolveState &st = a.st;
+  st.qutk[b] = QuTk;
+  st.ktquuk[b] = kTQuuk;
+  const int it = st.bwd[b];  // this problem's iteration index i of ilqr.hh:58
+  st.bwd[b] = it + 1;
+  const double cost = st.cost[b];
+  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
+  if (it > 0 && is_converged(p, cost, expected_new_cost)) {
+    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
+    st.phase[b] = PHASE_DONE;
+  } else if (it > 0 && p.ls_max_iters <= 0) {
+    // line_search's loop (ilqr.hh:178-193) runs zero candidates and throws
+    st.status[b] = QILQR_STATUS_LINE_SEARCH_FAILED;
+    st.phase[b] = PHASE_DONE;
+  } else {
+    st.alpha[b] = 1.0;
+    st.ls_iter[b] = 0;
+    st.phase[b] = (a.wide && it > 0) ? PHASE_WIDE : PHASE_SEARCH;  // iteration 0 is an unconditional full step
+  }
+}
 
 // Cost derivatives at one knot (cost.hh:47-57) in block form.
 //   J = blkdiag([[Ji, Qi], [0, Ji]], I6);  C.x = ((2 dx^T) Q) J;  C.xx = ((2 J^T) Q) J
@@ -520,7 +573,7 @@ QD void cost_derivatives(const DeviceParams &p, const double *dx, const double *
   for (int j = 0; j < 12; ++j) {
     double s = (2.0 * dx[0]) * p.Q[j];
 #pragma unroll
-    for (int i = 1; i < 12; ++i) s = fma(2.0 * dx[i], p.Q[12 * i + j], s);
+    for (int i = 1; i < 12; ++i) s = QFMA(2.0 * dx[i], p.Q[12 * i + j], s);
     y[j] = s;
   }
   m3T_vec(Ji, y, Cx);
@@ -535,12 +588,12 @@ QD void cost_derivatives(const DeviceParams &p, const double *dx, const double *
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       // row i (<3): sum_k 2*Ji[k][i] Q[k][j]
-      P[12 * i + j] = fma(2.0 * Ji[6 + i], p.Q[24 + j], fma(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
+      P[12 * i + j] = QFMA(2.0 * Ji[6 + i], p.Q[24 + j], QFMA(2.0 * Ji[3 + i], p.Q[12 + j], (2.0 * Ji[i]) * p.Q[j]));
       // row 3+i: sum_k 2*Qi[k][i] Q[k][j] + sum_k 2*Ji[k][i] Q[3+k][j]
-      double s = fma(2.0 * Qi[6 + i], p.Q[24 + j], fma(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
-      s = fma(2.0 * Ji[i], p.Q[36 + j], s);
-      s = fma(2.0 * Ji[3 + i], p.Q[48 + j], s);
-      s = fma(2.0 * Ji[6 + i], p.Q[60 + j], s);
+      double s = QFMA(2.0 * Qi[6 + i], p.Q[24 + j], QFMA(2.0 * Qi[3 + i], p.Q[12 + j], (2.0 * Qi[i]) * p.Q[j]));
+      s = QFMA(2.0 * Ji[i], p.Q[36 + j], s);
+      s = QFMA(2.0 * Ji[3 + i], p.Q[48 + j], s);
+      s = QFMA(2.0 * Ji[6 + i], p.Q[60 + j], s);
       P[12 * (3 + i) + j] = s;
     }
 #pragma unroll
@@ -551,11 +604,11 @@ QD void cost_derivatives(const DeviceParams &p, const double *dx, const double *
   for (int i = 0; i < 12; ++i) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      bel(Cxx, i, j) = fma(P[12 * i + 2], Ji[6 + j], fma(P[12 * i + 1], Ji[3 + j], P[12 * i] * Ji[j]));
-      double s = fma(P[12 * i + 2], Qi[6 + j], fma(P[12 * i + 1], Qi[3 + j], P[12 * i] * Qi[j]));
-      s = fma(P[12 * i + 3], Ji[j], s);
-      s = fma(P[12 * i + 4], Ji[3 + j], s);
-      s = fma(P[12 * i + 5], Ji[6 + j], s);
+      bel(Cxx, i, j) = QFMA(P[12 * i + 2], Ji[6 + j], QFMA(P[12 * i + 1], Ji[3 + j], P[12 * i] * Ji[j]));
+      double s = QFMA(P[12 * i + 2], Qi[6 + j], QFMA(P[12 * i + 1], Qi[3 + j], P[12 * i] * Qi[j]));
+      s = QFMA(P[12 * i + 3], Ji[j], s);
+      s = QFMA(P[12 * i + 4], Ji[3 + j], s);
+      s = QFMA(P[12 * i + 5], Ji[6 + j], s);
       bel(Cxx, i, 3 + j) = s;
     }
 #pragma unroll
@@ -601,7 +654,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
       for (int j = 0; j < 4; ++j) {
         double s = (2.0 * du[0]) * p.R[j];
 #pragma unroll
-        for (int l = 1; l < 4; ++l) s = fma(2.0 * du[l], p.R[4 * l + j], s);
+        for (int l = 1; l < 4; ++l) s = QFMA(2.0 * du[l], p.R[4 * l + j], s);
         Cu[j] = s;
       }
     }
@@ -650,7 +703,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
       for (int j = 0; j < 4; ++j) {
         double acc = bel(M, s, 8) * p.Bu[j];
 #pragma unroll
-        for (int c = 1; c < 4; ++c) acc = fma(bel(M, s, 8 + c), p.Bu[4 * c + j], acc);
+        for (int c = 1; c < 4; ++c) acc = QFMA(bel(M, s, 8 + c), p.Bu[4 * c + j], acc);
         Qxu[4 * s + j] = acc;
       }
     // Q.uu = C.uu + (B^T V) B
@@ -664,7 +717,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
         for (int c = 0; c < 4; ++c) {
           double acc = p.Bu[j] * bel(V, 8, 8 + c);
 #pragma unroll
-          for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + j], bel(V, 8 + r, 8 + c), acc);
+          for (int r = 1; r < 4; ++r) acc = QFMA(p.Bu[4 * r + j], bel(V, 8 + r, 8 + c), acc);
           BtV[4 * j + c] = acc;
         }
 #pragma unroll
@@ -673,8 +726,8 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
         for (int l = 0; l < 4; ++l) {
           double acc = BtV[4 * j] * p.Bu[l];
 #pragma unroll
-          for (int c = 1; c < 4; ++c) acc = fma(BtV[4 * j + c], p.Bu[4 * c + l], acc);
-          Quu[4 * j + l] = 2.0 * p.R[4 * j + l] + acc;
+          for (int c = 1; c < 4; ++c) acc = QFMA(BtV[4 * j + c], p.Bu[4 * c + l], acc);
+          Quu[4 * j + l] = QFMA(2.0, p.R[4 * j + l], acc);
         }
       if (p.quu_reg != 0.0) {
 #pragma unroll
@@ -701,7 +754,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
       for (int j = 0; j < 4; ++j) {
         double acc = p.Bu[j] * vx[8];
 #pragma unroll
-        for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + j], vx[8 + r], acc);
+        for (int r = 1; r < 4; ++r) acc = QFMA(p.Bu[4 * r + j], vx[8 + r], acc);
         Qu[j] = Cu[j] + acc;
       }
     }
@@ -736,14 +789,14 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
       for (int l = 0; l < 4; ++l) {
         double acc = K[s] * Quu[l];
 #pragma unroll
-        for (int j = 1; j < 4; ++j) acc = fma(K[12 * j + s], Quu[4 * j + l], acc);
+        for (int j = 1; j < 4; ++j) acc = QFMA(K[12 * j + s], Quu[4 * j + l], acc);
         KtQ[4 * s + l] = acc;
       }
 #pragma unroll
     for (int s = 0; s < 12; ++s) {
       double acc = KtQ[4 * s] * k[0];
 #pragma unroll
-      for (int l = 1; l < 4; ++l) acc = fma(KtQ[4 * s + l], k[l], acc);
+      for (int l = 1; l < 4; ++l) acc = QFMA(KtQ[4 * s + l], k[l], acc);
       vx[s] = Qx[s] - acc;
     }
 #pragma unroll
@@ -752,7 +805,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
       for (int c = 0; c < 12; ++c) {
         double acc = KtQ[4 * s] * K[c];
 #pragma unroll
-        for (int l = 1; l < 4; ++l) acc = fma(KtQ[4 * s + l], K[12 * l + c], acc);
+        for (int l = 1; l < 4; ++l) acc = QFMA(KtQ[4 * s + l], K[12 * l + c], acc);
         bel(V, s, c) = bel(Qxx, s, c) - acc;
       }
     if (p.symmetrize_vxx) {
@@ -771,42 +824,24 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
     {
       double acc = Qu[0] * k[0];
 #pragma unroll
-      for (int j = 1; j < 4; ++j) acc = fma(Qu[j], k[j], acc);
+      for (int j = 1; j < 4; ++j) acc = QFMA(Qu[j], k[j], acc);
       QuTk = QuTk + acc;
       double z[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         double s = k[0] * Quu[l];
 #pragma unroll
-        for (int j = 1; j < 4; ++j) s = fma(k[j], Quu[4 * j + l], s);
+        for (int j = 1; j < 4; ++j) s = QFMA(k[j], Quu[4 * j + l], s);
         z[l] = s;
       }
       double acc2 = z[0] * k[0];
 #pragma unroll
-      for (int l = 1; l < 4; ++l) acc2 = fma(z[l], k[l], acc2);
+      for (int l = 1; l < 4; ++l) acc2 = QFMA(z[l], k[l], acc2);
       kTQuuk = kTQuuk + acc2;
     }
   }
 
-  if (!a.solve_mode) {
-    a.terms_out[2 * size_t(b)] = QuTk;
-    a.terms_out[2 * size_t(b) + 1] = kTQuuk;
-    return;
-  }
-  const SolveState &st = a.st;
-  st.qutk[b] = QuTk;
-  st.ktquuk[b] = kTQuuk;
-  st.bwd[b] += 1;
-  const double cost = st.cost[b];
-  const double expected_new_cost = cost + (QuTk + kTQuuk / 2.0);  // ilqr.hh:64-65 with step = 1
-  if (a.iter > 0 && is_converged(p, cost, expected_new_cost)) {
-    st.status[b] = QILQR_STATUS_CONVERGED_EXPECTED;  // ilqr.hh:66-68
-    st.phase[b] = PHASE_DONE;
-  } else {
-    st.alpha[b] = 1.0;
-    st.ls_iter[b] = 0;
-    st.phase[b] = a.search_phase;
-  }
+  backward_finish(p, a, b, QuTk, kTQuuk);
 }
 
 // ---------------------------------------------------------------------------
@@ -821,6 +856,7 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int b = list ? list[t] : t;
+  if (st.phase[b] != PHASE_WIDE) return;  // `list` is the list of alive problems
   const double cur_cost = st.cost[b], qutk = st.qutk[b], ktq = st.ktquuk[b];
   double alpha = st.alpha[b];
   const int ls0 = st.ls_iter[b];
@@ -856,9 +892,13 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
 //   out_search <- entries with phase == SEARCH,  out_active <- phase == ACTIVE
 //   counts[0] = |out_search|, counts[1] = |out_active|   (mapped pinned host memory)
 // ---------------------------------------------------------------------------
+// mask_s / mask_a: bit ph set = problems in phase ph go to out_search / out_active (a problem may go to both)
+QD bool phase_in(int mask, int ph) { return ph >= 0 && ((mask >> ph) & 1); }
+constexpr int kMaskSearch = 1 << PHASE_SEARCH, kMaskActive = 1 << PHASE_ACTIVE, kMaskWide = 1 << PHASE_WIDE;
+constexpr int kMaskAlive = kMaskSearch | kMaskActive | kMaskWide;  // everything but PHASE_DONE
 __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, const int *phase, int *out_search,
-                                                 int *out_active, volatile int *counts, int phase_s = PHASE_SEARCH,
-                                                 int phase_a = PHASE_ACTIVE, int seq = 0) {
+                                                 int *out_active, volatile int *counts, int phase_s = kMaskSearch,
+                                                 int phase_a = kMaskActive, int seq = 0) {
   __shared__ int warp_s[32], warp_a[32];
   __shared__ int base_s, base_a;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;  // any multiple of 32 threads
@@ -871,8 +911,8 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
       b = list_in ? list_in[idx] : idx;
       ph = phase[b];
     }
-    const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
-    const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
+    const unsigned ms = __ballot_sync(0xffffffffu, phase_in(phase_s, ph));
+    const unsigned ma = __ballot_sync(0xffffffffu, phase_in(phase_a, ph));
     if (lane == 0) { warp_s[wid] = __popc(ms); warp_a[wid] = __popc(ma); }
     __syncthreads();
     if (wid == 0) {
@@ -888,8 +928,8 @@ __global__ void __launch_bounds__(1024) k_compact(const int *list_in, int n_in, 
     __syncthreads();
     const int off_s = base_s + (wid ? warp_s[wid - 1] : 0) + __popc(ms & ((1u << lane) - 1));
     const int off_a = base_a + (wid ? warp_a[wid - 1] : 0) + __popc(ma & ((1u << lane) - 1));
-    if (ph == phase_s) out_search[off_s] = b;
-    if (ph == phase_a) out_active[off_a] = b;
+    if (phase_in(phase_s, ph)) out_search[off_s] = b;
+    if (phase_in(phase_a, ph)) out_active[off_a] = b;
     __syncthreads();
     if (tid == 0) { base_s += warp_s[31]; base_a += warp_a[31]; }
     __syncthreads();
@@ -911,8 +951,8 @@ __global__ void __launch_bounds__(1024) k_compact_count(const int *list_in, int 
   const int idx = blockIdx.x * 1024 + tid;
   int ph = -1;
   if (idx < n_in) ph = phase[list_in ? list_in[idx] : idx];
-  const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
-  const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
+  const unsigned ms = __ballot_sync(0xffffffffu, phase_in(phase_s, ph));
+  const unsigned ma = __ballot_sync(0xffffffffu, phase_in(phase_a, ph));
   if (lane == 0) { ws[wid] = __popc(ms); wa[wid] = __popc(ma); }
   __syncthreads();
   if (wid == 0) {
@@ -962,8 +1002,8 @@ __global__ void __launch_bounds__(1024) k_compact_scatter(const int *list_in, in
   const int idx = blockIdx.x * 1024 + tid;
   int b = -1, ph = -1;
   if (idx < n_in) { b = list_in ? list_in[idx] : idx; ph = phase[b]; }
-  const unsigned ms = __ballot_sync(0xffffffffu, ph == phase_s);
-  const unsigned ma = __ballot_sync(0xffffffffu, ph == phase_a);
+  const unsigned ms = __ballot_sync(0xffffffffu, phase_in(phase_s, ph));
+  const unsigned ma = __ballot_sync(0xffffffffu, phase_in(phase_a, ph));
   __syncthreads();
   if (lane == 0) { ws[wid] = __popc(ms); wa[wid] = __popc(ma); }
   __syncthreads();
@@ -979,32 +1019,49 @@ __global__ void __launch_bounds__(1024) k_compact_scatter(const int *list_in, in
   __syncthreads();
   const int off_s = base_s + (wid ? ws[wid - 1] : 0) + __popc(ms & ((1u << lane) - 1));
   const int off_a = base_a + (wid ? wa[wid - 1] : 0) + __popc(ma & ((1u << lane) - 1));
-  if (ph == phase_s) out_search[off_s] = b;
-  if (ph == phase_a) out_active[off_a] = b;
+  if (phase_in(phase_s, ph)) out_search[off_s] = b;
+  if (phase_in(phase_a, ph)) out_active[off_a] = b;
 }
 
 // ---------------------------------------------------------------------------
 // Solve set-up / tear-down
 // ---------------------------------------------------------------------------
-__global__ void k_init_state(SolveState st, int B) {
+// max_iters: the loop bound of ilqr.hh:58 for i = 0 (a non-positive or NaN bound runs no iteration at all)
+__global__ void k_init_state(SolveState st, int B, double max_iters) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   st.new_cost[b] = 0.0; st.qutk[b] = 0.0; st.ktquuk[b] = 0.0; st.alpha[b] = 1.0;
   st.ls_iter[b] = 0; st.status[b] = QILQR_STATUS_NOT_RUN; st.bwd[b] = 0; st.rollouts[b] = 0;
-  st.ndebug[b] = 0; st.sel[b] = 0; st.phase[b] = PHASE_ACTIVE; st.accepted_iter[b] = -1;
+  st.ndebug[b] = 0; st.sel[b] = 0; st.phase[b] = (0.0 < max_iters) ? PHASE_ACTIVE : PHASE_DONE;
+  st.accepted_iter[b] = -1;
 }
 // Problems still running after the loop bound hit max_iters (ilqr.hh:58,86); writes results.
-__global__ void k_finalize(SolveState st, int B, qilqr_result_t *res) {
+// totals[0] += sum of backward passes, totals[1] += sum of rollouts (the solver's statistics).
+__global__ void k_finalize(SolveState st, int B, qilqr_result_t *res, unsigned long long *totals) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  int s = st.status[b];
-  if (s == QILQR_STATUS_NOT_RUN) { s = QILQR_STATUS_MAX_ITERS; st.status[b] = s; }
-  if (res) {
-    res[b].status = s;
-    res[b].backward_passes = st.bwd[b];
-    res[b].rollouts = st.rollouts[b];
-    res[b].num_debug = st.ndebug[b];
-    res[b].final_cost = st.cost[b];
+  int nb = 0, nr = 0;
+  if (b < B) {
+    int s = st.status[b];
+    if (s == QILQR_STATUS_NOT_RUN) { s = QILQR_STATUS_MAX_ITERS; st.status[b] = s; }
+    nb = st.bwd[b];
+    nr = st.rollouts[b];
+    if (res) {
+      res[b].status = s;
+      res[b].backward_passes = nb;
+      res[b].rollouts = nr;
+      res[b].num_debug = st.ndebug[b];
+      res[b].final_cost = st.cost[b];
+    }
+  }
+  if (!totals) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    nr += __shfl_xor_sync(0xffffffffu, nr, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&totals[0], (unsigned long long)nb);
+    atomicAdd(&totals[1], (unsigned long long)nr);
   }
 }
 // Copy the current trajectory of the problems whose result sits in buf1 back to buf0.
@@ -1033,6 +1090,11 @@ __global__ void k_tail_gather(Problem big, SolveState sb, Problem mini, SolveSta
   }
   for (int r = blockIdx.y; r < sb.hist_cap; r += gridDim.y)
     if (sb.cost_hist) sm.cost_hist[size_t(r) * m + t] = sb.cost_hist[size_t(r) * B + b];
+  if (sb.phase[b] != PHASE_ACTIVE) {
+    // in the middle of its line search: the gains of its last backward pass are still needed
+    for (int r = blockIdx.y; r < big.N * 4; r += gridDim.y) mini.gk[size_t(r) * m + t] = big.gk[size_t(r) * B + b];
+    for (int r = blockIdx.y; r < big.N * 48; r += gridDim.y) mini.gK[size_t(r) * m + t] = big.gK[size_t(r) * B + b];
+  }
   if (blockIdx.y != 0) return;
   sm.cost[t] = sb.cost[b]; sm.new_cost[t] = sb.new_cost[b]; sm.qutk[t] = sb.qutk[b]; sm.ktquuk[t] = sb.ktquuk[b];
   sm.alpha[t] = sb.alpha[b];
@@ -1150,7 +1212,7 @@ __global__ void k_api_cost(const __grid_constant__ DeviceParams p, int B, const 
   if (C_u)
     for (int j = 0; j < 4; ++j) {
       double s = (2.0 * du[0]) * p.R[j];
-      for (int l = 1; l < 4; ++l) s = fma(2.0 * du[l], p.R[4 * l + j], s);
+      for (int l = 1; l < 4; ++l) s = QFMA(2.0 * du[l], p.R[4 * l + j], s);
       C_u[size_t(b) * 4 + j] = s;
     }
   if (C_uu) for (int e = 0; e < 16; ++e) C_uu[size_t(b) * 16 + e] = 2.0 * p.R[e];

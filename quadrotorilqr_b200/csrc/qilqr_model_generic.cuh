@@ -30,9 +30,9 @@ QD void continuous(const DeviceParams &p, const double *x /*13*/, const double *
   body_acceleration(p, R, x + 7, u, xdot + 6);
   if (p.coriolis) {
     const double *v = x + 7, *w = x + 10;
-    xdot[6] = xdot[6] + fma(v[1], w[2], -(v[2] * w[1]));
-    xdot[7] = xdot[7] + fma(v[2], w[0], -(v[0] * w[2]));
-    xdot[8] = xdot[8] + fma(v[0], w[1], -(v[1] * w[0]));
+    xdot[6] = xdot[6] + QFMA(v[1], w[2], -(v[2] * w[1]));
+    xdot[7] = xdot[7] + QFMA(v[2], w[0], -(v[0] * w[2]));
+    xdot[8] = xdot[8] + QFMA(v[0], w[1], -(v[1] * w[0]));
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) xdot[i] = x[7 + i];
@@ -54,7 +54,7 @@ QD void euler_state(const double *x /*13*/, const double *k /*12*/, double dt, d
 #pragma unroll
   for (int i = 0; i < 4; ++i) xn[3 + i] = qn[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) xn[7 + i] = x[7 + i] + dt * k[6 + i];
+  for (int i = 0; i < 6; ++i) xn[7 + i] = QFMA(dt, k[6 + i], x[7 + i]);
 }
 
 // discrete_dynamics without derivatives for any variant; x is advanced in place
@@ -81,7 +81,7 @@ QD void discrete_step_any(const DeviceParams &p, double *x /*13*/, const double 
     euler_state(x, k, dti, xi);
     continuous(p, xi, u, k);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) xdot[e] = xdot[e] + ci * k[e];
+    for (int e = 0; e < 12; ++e) xdot[e] = QFMA(ci, k[e], xdot[e]);
   }
   euler_state(x, xdot, p.dt, x);
 }
@@ -113,7 +113,7 @@ QD void euler_with_blocks(const double *x, const double *k, double dt, double *x
 #pragma unroll
   for (int i = 0; i < 4; ++i) xn[3 + i] = qn[i];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) xn[7 + i] = x[7 + i] + dt * k[6 + i];
+  for (int i = 0; i < 6; ++i) xn[7 + i] = QFMA(dt, k[6 + i], x[7 + i]);
 }
 QD void continuous_with_blocks(const DeviceParams &p, const double *x, const double *u, double *xdot, ContBlocks &F) {
   continuous(p, x, u, xdot);
@@ -139,9 +139,9 @@ QD void strip_mul(const double *blk, const double *X, double *out) {
     const double x0 = X[c], x1 = X[n + c], x2 = X[2 * n + c];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      double s = ACC ? fma(blk[3 * i], x0, out[i * n + c]) : blk[3 * i] * x0;
-      s = fma(blk[3 * i + 1], x1, s);
-      out[i * n + c] = fma(blk[3 * i + 2], x2, s);
+      double s = ACC ? QFMA(blk[3 * i], x0, out[i * n + c]) : blk[3 * i] * x0;
+      s = QFMA(blk[3 * i + 1], x1, s);
+      out[i * n + c] = QFMA(blk[3 * i + 2], x2, s);
     }
   }
 }
@@ -270,7 +270,7 @@ QD void discrete_stages(const DeviceParams &p, const double *x, const double *u,
     continuous_with_blocks(p, xi, u, k, F);
     compact(F, W.Fs[i]);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) xdot[e] = xdot[e] + ci * k[e];
+    for (int e = 0; e < 12; ++e) xdot[e] = QFMA(ci, k[e], xdot[e]);
   }
   euler_with_blocks(x, xdot, p.dt, xn, W.Es[3]);
 }
@@ -303,7 +303,7 @@ QD void jacobian_strip(const DeviceParams &p, const StageBlocks &W, int s, doubl
         for (int e = 0; e < 16; ++e) D[32 + e] = D[32 + e] + p.JuC[e];
       }
 #pragma unroll
-      for (int e = 0; e < 12 * n; ++e) S[e] = S[e] + ci * D[e];
+      for (int e = 0; e < 12 * n; ++e) S[e] = QFMA(ci, D[e], S[e]);
     }
     euler_rhs_mul<n>(W.Es[3], S, T);
   }

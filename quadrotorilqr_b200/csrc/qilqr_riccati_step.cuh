@@ -4,6 +4,8 @@
 // memory, stride RS = 1) and the split kernel (k_riccati_g4: record tiles [elem][8 problems]
 // brought in by TMA bulk copies, stride RS = 8).  See qilqr_backward_g4.cuh for the algorithm.
 //   rec    : this knot's linearisation record, element e at rec[e * RS]
+//   valid  : write this problem's gains (false for the padding quads of the last tile, and for quads of the
+//            persistent tail kernel whose problem is not in its backward pass)
 //   s2Qvv  : 2*Q_vv (6x6), dense
 //   xch    : this problem's exchange area (g4::XCH doubles)
 //   V0..V3 : the lane's column block c of V_xx (in/out);  vx: v_x (replicated, in/out)
@@ -65,7 +67,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
       for (int cc = 0; cc < 4; ++cc) {
         double acc = p.Bu[jj] * V88[cc];
 #pragma unroll
-        for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + jj], V88[4 * r + cc], acc);
+        for (int r = 1; r < 4; ++r) acc = QFMA(p.Bu[4 * r + jj], V88[4 * r + cc], acc);
         BtV[4 * jj + cc] = acc;
       }
 #pragma unroll
@@ -74,8 +76,8 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
       for (int l = 0; l < 4; ++l) {
         double acc = BtV[4 * jj] * p.Bu[l];
 #pragma unroll
-        for (int cc = 1; cc < 4; ++cc) acc = fma(BtV[4 * jj + cc], p.Bu[4 * cc + l], acc);
-        Quu[4 * jj + l] = 2.0 * p.R[4 * jj + l] + acc;
+        for (int cc = 1; cc < 4; ++cc) acc = QFMA(BtV[4 * jj + cc], p.Bu[4 * cc + l], acc);
+        Quu[4 * jj + l] = QFMA(2.0, p.R[4 * jj + l], acc);
       }
     if (p.quu_reg != 0.0) {
 #pragma unroll
@@ -85,7 +87,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     for (int jj = 0; jj < 4; ++jj) {
       double acc = p.Bu[jj] * vx[8];
 #pragma unroll
-      for (int r = 1; r < 4; ++r) acc = fma(p.Bu[4 * r + jj], vx[8 + r], acc);
+      for (int r = 1; r < 4; ++r) acc = QFMA(p.Bu[4 * r + jj], vx[8 + r], acc);
       Qu[jj] = rec[(R_CU + jj) * RS] + acc;
     }
     // Q.x = C.x + A^T v_x
@@ -98,9 +100,9 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     m3T_vec_add(Ab, vx + 3, T + 3);
     {  // += dG^T vx[6:9] = hat(-dgz) vx[6:9]
       const double *v = vx + 6;
-      T[3] += fma(ndgz[1], v[2], -(ndgz[2] * v[1]));
-      T[4] += fma(ndgz[2], v[0], -(ndgz[0] * v[2]));
-      T[5] += fma(ndgz[0], v[1], -(ndgz[1] * v[0]));
+      T[3] = QFMA(ndgz[1], v[2], QFMA(-ndgz[2], v[1], T[3]));
+      T[4] = QFMA(-ndgz[0], v[2], QFMA(ndgz[2], v[0], T[4]));
+      T[5] = QFMA(ndgz[0], v[1], QFMA(-ndgz[1], v[0], T[5]));
     }
     ld9s<RS>(rec + R_DJR * RS, Ab);
     m3T_vec(Ab, vx, T + 6);
@@ -191,7 +193,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
       for (int jj = 0; jj < 4; ++jj) {
         double acc = X2[3 * s + 2] * p.Bu[jj];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) acc = fma(X3[3 * s + cc], p.Bu[4 * (1 + cc) + jj], acc);
+        for (int cc = 0; cc < 3; ++cc) acc = QFMA(X3[3 * s + cc], p.Bu[4 * (1 + cc) + jj], acc);
         Qxu[4 * s + jj] = acc;
       }
   }
@@ -213,14 +215,14 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
       for (int l = 0; l < 4; ++l) {
         double acc = Ks[s] * Quu[l];
 #pragma unroll
-        for (int jj = 1; jj < 4; ++jj) acc = fma(Ks[3 * jj + s], Quu[4 * jj + l], acc);
+        for (int jj = 1; jj < 4; ++jj) acc = QFMA(Ks[3 * jj + s], Quu[4 * jj + l], acc);
         KQ[4 * s + l] = acc;
       }
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       double acc = KQ[4 * s] * k[0];
 #pragma unroll
-      for (int l = 1; l < 4; ++l) acc = fma(KQ[4 * s + l], k[l], acc);
+      for (int l = 1; l < 4; ++l) acc = QFMA(KQ[4 * s + l], k[l], acc);
       const double qx = (c == 0) ? Qx[s] : (c == 1) ? Qx[3 + s] : (c == 2) ? Qx[6 + s] : Qx[9 + s];
       xch[X_VX + 3 * c + s] = qx - acc;
     }
@@ -229,9 +231,9 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         xch[X_K + 12 * jj + 3 * c + s] = Ks[3 * jj + s];
-        a.pr.gK[row_index(ii, 12 * jj + 3 * c + s, 48, B, b)] = Ks[3 * jj + s];  // tail quads rewrite identical values
+        if (valid) a.pr.gK[row_index(ii, 12 * jj + 3 * c + s, 48, B, b)] = Ks[3 * jj + s];
       }
-    {
+    if (valid) {
       const double kc = (c == 0) ? k[0] : (c == 1) ? k[1] : (c == 2) ? k[2] : k[3];
       a.pr.gk[row_index(ii, c, 4, B, b)] = kc;
     }
@@ -251,10 +253,10 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
                a3 = KQ[4 * s] * Kall[9 + cc];
 #pragma unroll
         for (int l = 1; l < 4; ++l) {
-          a0 = fma(KQ[4 * s + l], Kall[12 * l + cc], a0);
-          a1 = fma(KQ[4 * s + l], Kall[12 * l + 3 + cc], a1);
-          a2 = fma(KQ[4 * s + l], Kall[12 * l + 6 + cc], a2);
-          a3 = fma(KQ[4 * s + l], Kall[12 * l + 9 + cc], a3);
+          a0 = QFMA(KQ[4 * s + l], Kall[12 * l + cc], a0);
+          a1 = QFMA(KQ[4 * s + l], Kall[12 * l + 3 + cc], a1);
+          a2 = QFMA(KQ[4 * s + l], Kall[12 * l + 6 + cc], a2);
+          a3 = QFMA(KQ[4 * s + l], Kall[12 * l + 9 + cc], a3);
         }
         Q0[3 * s + cc] -= a0;
         Q1[3 * s + cc] -= a1;
@@ -270,15 +272,15 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     // expected cost reduction terms (ilqr.hh:136-140), replicated
     double acc = Qu[0] * k[0];
 #pragma unroll
-    for (int jj = 1; jj < 4; ++jj) acc = fma(Qu[jj], k[jj], acc);
+    for (int jj = 1; jj < 4; ++jj) acc = QFMA(Qu[jj], k[jj], acc);
     QuTk = QuTk + acc;
     double acc2 = 0.0;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       double z = k[0] * Quu[l];
 #pragma unroll
-      for (int jj = 1; jj < 4; ++jj) z = fma(k[jj], Quu[4 * jj + l], z);
-      acc2 = (l == 0) ? z * k[0] : fma(z, k[l], acc2);
+      for (int jj = 1; jj < 4; ++jj) z = QFMA(k[jj], Quu[4 * jj + l], z);
+      acc2 = (l == 0) ? z * k[0] : QFMA(z, k[l], acc2);
     }
     kTQuuk = kTQuuk + acc2;
   }

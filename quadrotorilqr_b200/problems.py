@@ -171,3 +171,34 @@ def figure_eight_desired(n_knots=1000, dt_s=0.02, amp_m=2.0, period_s=20.0, mass
     d[:, 7] = 1.0
     d[:, 14:18] = mass_kg * g_mpss / 4.0
     return d
+
+
+# ---------------------------------------------------------------------------------
+# C3 "waypoint" variant and C4 initial states (SURVEY.md section 8d)
+# ---------------------------------------------------------------------------------
+def waypoint_desired_trajectories(batch, n_knots=40, dt_s=0.1, mass_kg=1.0, g_mpss=9.81, seed=3, first=0,
+                                  segments=4):
+    """[batch, n_knots, 18]: every problem tracks its own piecewise-constant position path of `segments`
+    waypoints drawn U[-1,1]^3 (identity attitude, zero velocity, hover thrust) -- one desired trajectory
+    per problem (``desired_count = batch``).  Counter-based like :func:`hover_initial_states`: problem b
+    gets the same waypoints whatever the batch or rank (12 uniforms = 3 Philox steps per problem)."""
+    assert segments == 4, "12 uniforms per problem"
+    bitgen = np.random.Philox(key=seed)
+    bitgen.advance(int(first) * 3)
+    way = 2.0 * np.random.Generator(bitgen).random((batch, segments, 3)) - 1.0
+    base = hover_desired_trajectory(n_knots, dt_s, mass_kg, g_mpss)
+    desired = np.repeat(base[None], batch, axis=0)
+    for seg in range(segments):
+        desired[:, seg * n_knots // segments:(seg + 1) * n_knots // segments, 1:4] = way[:, seg][:, None, :]
+    return desired
+
+
+def figure_eight_initial_states(batch, desired, seed=4, first=0, pos=0.3):
+    """C4: x0 = first desired state with the position perturbed by U[-pos,pos]^3 (counter-based, 4 draws
+    = one Philox step per problem, the fourth unused)."""
+    bitgen = np.random.Philox(key=seed)
+    bitgen.advance(int(first))
+    u = np.random.Generator(bitgen).random((batch, 4))
+    x0 = np.tile(np.asarray(desired)[0, 1:14], (batch, 1))
+    x0[:, 0:3] += (2.0 * u[:, 0:3] - 1.0) * pos
+    return x0

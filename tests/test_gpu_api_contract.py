@@ -78,7 +78,10 @@ def test_solver_reuse_and_option_changes(O):
     assert np.array_equal(r3["traj"], first["traj"])
     st = s.last_solve_stats()
     assert st["problem_iterations"] == int(r3["results"]["backward_passes"].sum())
-    assert st["solver_iterations"] == int(r3["results"]["backward_passes"].max())
+    assert st["problem_rollouts"] == int(r3["results"]["rollouts"].sum())
+    # host-sequenced super-steps: none beyond the slowest problem's rollouts (the persistent tail kernel, which takes
+    # over small batches from the start, does not count)
+    assert 0 <= st["solver_iterations"] <= int(r3["results"]["rollouts"].max())
 
 
 def test_concurrent_handles_do_not_interfere():

@@ -96,10 +96,7 @@ def main():
         s = mk(m, o)
         N, B = 40, 65536
         base = problems.hover_desired_trajectory(N)
-        way = np.random.Generator(np.random.Philox(key=3)).uniform(-1, 1, (B, 4, 3))  # waypoints U[-1,1]^3
-        desired = np.repeat(base[None], B, axis=0)
-        for seg in range(4):
-            desired[:, seg * N // 4:(seg + 1) * N // 4, 1:4] = way[:, seg][:, None, :]
+        desired = problems.waypoint_desired_trajectories(B, N)  # waypoints U[-1,1]^3
         _, init, _ = device_problem(s, problems.hover_initial_states(B, seed=2026), base, N, dev)
         des = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
         s.pack_trajectory_device(torch.from_numpy(desired).to(dev), des)
@@ -118,8 +115,7 @@ def main():
         o = dataclasses.replace(problems.default_options(False), symmetrize_vxx=True, num_parallel_alphas=8)
         s = mk(m, o)
         d = problems.figure_eight_desired(N, dt_s)
-        x0 = np.tile(d[0, 1:14], (B, 1))
-        x0[:, 0:3] += np.random.Generator(np.random.Philox(key=4)).uniform(-0.3, 0.3, (B, 3))
+        x0 = problems.figure_eight_initial_states(B, d)
         _, init, des = device_problem(s, x0, d, N, dev)
         dt, res = time_solves(s, init, des, 2)
         conv = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
