@@ -37,6 +37,13 @@ if ROOT not in sys.path:
 METRIC = "converged iLQR solves/sec (batch 65536 per GPU, N=40 hover problems, FP64)"
 UNIT = "solves/s"
 N_KNOTS = 40
+
+
+def workload_string(batch, seed):
+    """config.workload -- the same string on the GPU arm and on the reference arm."""
+    return (f"batch {batch} hover problems/GPU, N={N_KNOTS}, dt=0.1, reference default options (rtol=atol=1e-12, "
+            "max_iters=100, line search 0.5/0.5/100), torque_to_thrust_ratio=0.1, x0: pos U[-1,1]^3, angle U[0,0.5] rad, "
+            f"vel U[-0.25,0.25]^6 (Philox seed {seed})")
 # dense as-written FLOPs per knot, counted by the oracle's FLOP-counting scalar
 # (oracle.count_flops on a converged hover trajectory; DESIGN.md section 5)
 F_BWD, F_ROLL, F_COST = 30231.3, 721.2, 581.2
@@ -160,9 +167,8 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batch {args.batch} hover problems/GPU, N={N_KNOTS}, dt=0.1, reference default "
-                               "options (rtol=atol=1e-12, max_iters=100), torque_to_thrust_ratio=0.1",
-                   "note": "CPU arm solves a bounded sample of that workload per step"},
+        "config": {"workload": workload_string(args.batch, args.seed),
+                   "sample": "the CPU arm solves a bounded sample of that workload per step (cpu_baseline.sample)"},
         "us_per_iteration": 1e6 * tot_t / max(1, tot_it),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,7 +195,10 @@ def main():
     ap.add_argument("--stagger-ms", type=float, default=-1.0,
                     help="start offset between pipelined handles (default: one measured step time; 0 = start together)")
     ap.add_argument("--pipeline", type=int, default=8,
-                    help="batches in flight per GPU (solver handles, each on its own stream/host thread)")
+                    help="batches in flight per GPU: host threads, each driving its own solver handle(s) and stream(s)")
+    ap.add_argument("--handles-per-thread", type=int, default=1, choices=[1, 2],
+                    help="2 = a thread begins its next batch on a second handle before finishing the previous one "
+                         "(useful with QILQR_PERSISTENT_TAIL=1; measured no faster on one B200, profiles/r2)")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -198,8 +207,6 @@ def main():
     # Two streams per handle: with the default 8 hardware queues, streams that share a queue serialise (a tail kernel
     # waits for another handle's bulk kernel to be dispatched).  Must be set before the CUDA context exists.
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-    if args.pipeline > 8:  # more host threads than a small box has cores to spare: sleep-poll while a batch is in its bulk
-        os.environ.setdefault("QILQR_BULK_POLL_US", "30")
 
     import torch
 
@@ -226,59 +233,76 @@ def main():
     B, N = args.batch, N_KNOTS
     P = max(1, args.pipeline)
 
+    H = max(1, args.handles_per_thread)
+
     def make_solver():
         s_ = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"],
                        m["Q"], m["R"], m["dt_s"], opts, device=local_rank, model_flags=args.model_variant)
         return s_
 
-    # P solver handles = a P-deep software pipeline of batches: each handle is driven by its own host
-    # thread on its own stream, so the latency-bound tail of one batch (the few problems that run to
-    # max_iters) overlaps the throughput-bound bulk of the next.  Every step is still one full batch.
-    solvers = [make_solver() for _ in range(P)]
-    streams = [torch.cuda.ExternalStream(s_.stream_handle, device=dev) for s_ in solvers]
-    solver = solvers[0]
+    # P host threads x H solver handles = a software pipeline of batches.  A thread begins a batch on one handle
+    # (qilqr_solve_*_begin returns once the device finishes the batch on its own: the few problems that creep to
+    # max_iters run in the persistent tail kernel), begins the next batch on its other handle, and only then
+    # finishes the first.  Every step is still one full batch, solved to the reference's own termination rule.
+    solvers = [[make_solver() for _ in range(H)] for _ in range(P)]
+    streams = [[torch.cuda.ExternalStream(s_.stream_handle, device=dev) for s_ in row] for row in solvers]
+    solver = solvers[0][0]
 
     # ---- synthetic inputs: this rank's problems [rank*B, (rank+1)*B) of the Philox stream ----
     desired = problems.hover_desired_trajectory(N, m["dt_s"], m["mass_kg"], m["g_mpss"])
     x0 = problems.hover_initial_states(B, seed=args.seed, first=rank * B)
     x0_soa = torch.from_numpy(np.ascontiguousarray(x0.T)).to(dev)  # [13][B]
     init_soa = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
-    work_soa = [torch.empty_like(init_soa) for _ in range(P)]
+    work_soa = [[torch.empty_like(init_soa) for _ in range(H)] for _ in range(P)]
     des_aos = torch.from_numpy(desired[None].copy()).to(dev)
     des_soa = torch.empty((N, 17, 1), dtype=torch.float64, device=dev)
-    res_dev = [torch.zeros(B * 24, dtype=torch.uint8, device=dev) for _ in range(P)]
+    res_dev = [[torch.zeros(B * 24, dtype=torch.uint8, device=dev) for _ in range(H)] for _ in range(P)]
     torch.cuda.synchronize()
     solver.pack_trajectory_device(des_aos, des_soa)
     solver.rollout_constant_control_device(x0_soa, desired[0, 14:18], init_soa)  # open-loop hover rollout
     torch.cuda.synchronize()
 
     STAT_KEYS = ("backward_ms", "rollout_ms", "backward_problem_knots", "rollout_problem_knots",
-                 "problem_iterations", "problem_rollouts", "solver_iterations", "bulk_wall_ms", "tail_wall_ms")
+                 "problem_iterations", "problem_rollouts", "solver_iterations", "bulk_wall_ms", "tail_wall_ms",
+                 "backward_ms_bulk", "rollout_ms_bulk", "backward_problem_knots_bulk", "kernel_launches")
 
-    def device_step(j, acc=None):
-        with torch.cuda.stream(streams[j]):
-            work_soa[j].copy_(init_soa, non_blocking=True)
-        solvers[j].solve_device(work_soa[j], des_soa, results=res_dev[j])
-        if acc is not None:
-            st = solvers[j].last_solve_stats()
-            for k_ in STAT_KEYS:
-                acc[k_] += st[k_]
+    def device_begin(j, h):
+        with torch.cuda.stream(streams[j][h]):
+            work_soa[j][h].copy_(init_soa, non_blocking=True)
+        solvers[j][h].solve_device_begin(work_soa[j][h], des_soa, results=res_dev[j][h])
 
-    def run_pipelined(step_fn, nsteps, stagger_s=0.0):
-        """Issue `nsteps` steps round-robin over the P handles, one host thread per handle.
+    def device_finish(j, h, acc):
+        solvers[j][h].solve_device_finish()
+        st = solvers[j][h].last_solve_stats()
+        for k_ in STAT_KEYS:
+            acc[k_] += st[k_]
 
-        `stagger_s`: handle j starts j * stagger_s late.  Handles that start together stay in lock step (they
-        share the GPU equally, so their throughput-bound phases end together) and then sit in their
-        latency-bound tails together with the GPU almost idle; started one step apart, one handle's tail
-        always overlaps another's bulk."""
+    def run_pipelined(begin_fn, finish_fn, nsteps, stagger_s=0.0):
+        """`nsteps` batches round-robin over the P threads; thread j alternates between its H handles and finishes
+        a batch only when it needs the handle again (or at the end).  `stagger_s`: thread j starts j * stagger_s
+        late (threads that start together stay in lock step)."""
         accs = [{k_: 0 for k_ in STAT_KEYS} for _ in range(P)]
         counts = [nsteps // P + (1 if j < nsteps % P else 0) for j in range(P)]
+        errors = []
 
         def worker(j):
-            if stagger_s > 0 and j > 0 and counts[j] > 0:
-                time.sleep(j * stagger_s)
-            for _ in range(counts[j]):
-                step_fn(j, accs[j])
+            try:
+                if stagger_s > 0 and j > 0 and counts[j] > 0:
+                    time.sleep(j * stagger_s)
+                pending = [False] * H
+                for s_ in range(counts[j]):
+                    h = s_ % H
+                    if pending[h]:
+                        finish_fn(j, h, accs[j])
+                    begin_fn(j, h)
+                    pending[h] = True
+                for d_ in range(H):  # oldest first
+                    h = (counts[j] + d_) % H
+                    if pending[h]:
+                        finish_fn(j, h, accs[j])
+                        pending[h] = False
+            except Exception as e:  # noqa: BLE001 -- re-raised on the main thread
+                errors.append(e)
 
         if P == 1:
             worker(0)
@@ -288,6 +312,8 @@ def main():
                 t_.start()
             for t_ in ths:
                 t_.join()
+        if errors:
+            raise errors[0]
         return {k_: sum(a_[k_] for a_ in accs) for k_ in STAT_KEYS}
 
     def barrier():
@@ -296,59 +322,66 @@ def main():
         torch.cuda.synchronize()
 
     # ---- `value`: device-resident ----------------------------------------------------------
-    n_warm = max(args.warmup, P)
-    run_pipelined(device_step, n_warm)  # first calls: allocation of the workspaces
+    n_warm = max(args.warmup, P * H)
+    run_pipelined(device_begin, device_finish, n_warm)  # first calls: allocation of the workspaces
     barrier()
     t_w0 = time.perf_counter()
-    run_pipelined(device_step, n_warm)
+    run_pipelined(device_begin, device_finish, n_warm)
     barrier()
-    # start offset between handles inside the timed regions: one step time (measured on the warm-up), unless given
+    # start offset between threads inside the timed regions: one step time (measured on the warm-up), unless given
     stagger_s = (args.stagger_ms * 1e-3 if args.stagger_ms >= 0 else (time.perf_counter() - t_w0) / n_warm) if P > 1 else 0.0
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = sum(s_.kernel_launch_count for s_ in solvers)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(P)]
     barrier()
     for j in range(P):
-        ev0[j].record(streams[j])
+        ev0[j].record(streams[j][0])
     t_wall0 = time.perf_counter()
-    tot = run_pipelined(device_step, args.steps, stagger_s)
+    tot = run_pipelined(device_begin, device_finish, args.steps, stagger_s)
     for j in range(P):
-        ev1[j].record(streams[j])
+        ev1[j].record(streams[j][0])
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = sum(s_.kernel_launch_count for s_ in solvers) - launches0
+    launches = tot["kernel_launches"]
     clocks = sampler.stop()
     dev_ms = max(ev0[j].elapsed_time(ev1[j]) for j in range(P))
     prob_iters, prob_rollouts, solver_iters = tot["problem_iterations"], tot["problem_rollouts"], tot["solver_iterations"]
-    res = np.frombuffer(res_dev[0].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    res = np.frombuffer(res_dev[0][0].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     converged = int(np.sum((res["status"] == 1) | (res["status"] == 2)))
     ls_failed = int(np.sum(res["status"] >= 4))
     max_iter_hit = int(np.sum(res["status"] == 3))
 
-    # One batch at a time on one handle (no pipelining): the latency of a single batch, and the place
-    # where the kernels are timed ALONE with CUDA events on the solver's stream (inside the pipelined
-    # region above kernels of different handles overlap, so per-kernel durations are not separable).
+    # One batch at a time on one handle (no pipelining): the latency of a single batch ...
+    def serial_steps(n_, acc):
+        t0_ = time.perf_counter()
+        for _ in range(n_):
+            device_begin(0, 0)
+            device_finish(0, 0, acc)
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - t0_) / n_
+
     barrier()
-    solvers[0].set_profiling(True)
-    ser = {k_: 0 for k_ in STAT_KEYS}
     n_serial = 3
-    t0 = time.perf_counter()
-    for _ in range(n_serial):
-        device_step(0, ser)
-    torch.cuda.synchronize()
-    serial_ms = 1e3 * (time.perf_counter() - t0) / n_serial
-    solvers[0].set_profiling(False)
+    serial_ms = serial_steps(n_serial, {k_: 0 for k_ in STAT_KEYS})
+    # ... and the place where the kernels are timed ALONE with CUDA events on the solver's stream around every
+    # launch (inside the pipelined region kernels of different handles overlap, so per-kernel durations are not
+    # separable).  Profiling keeps the host-driven loop to the end, so the latency-bound tail launches (a handful
+    # of problems each) are timed too and reported apart from the throughput-bound bulk launches.
+    solver.set_profiling(True)
+    ser = {k_: 0 for k_ in STAT_KEYS}
+    prof_ms = serial_steps(n_serial, ser)
+    solver.set_profiling(False)
     bwd_ms, roll_ms = ser["backward_ms"], ser["rollout_ms"]
     bwd_knots, roll_knots = ser["backward_problem_knots"], ser["rollout_problem_knots"]
+    bwd_ms_bulk, bwd_knots_bulk = ser["backward_ms_bulk"], ser["backward_problem_knots_bulk"]
 
-    # ---- `e2e`: host buffers through qilqr_solve_host ------------------------------------------
+    # ---- `e2e`: host buffers through qilqr_solve_host_begin / _finish -----------------------------------
     e2e = None
     if not args.no_e2e:
         init_host = torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True)
-        out_host = [torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True) for _ in range(P)]
-        res_host = [torch.zeros(B * 24, dtype=torch.uint8, pin_memory=True) for _ in range(P)]
+        out_host = [[torch.empty((B, N, 18), dtype=torch.float64, pin_memory=True) for _ in range(H)] for _ in range(P)]
+        res_host = [[torch.zeros(B * 24, dtype=torch.uint8, pin_memory=True) for _ in range(H)] for _ in range(P)]
         aos = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
         solver.unpack_trajectory_device(init_soa, aos, time_src=None)
@@ -358,17 +391,20 @@ def main():
         del aos
         desired_c = np.ascontiguousarray(desired)
 
-        def host_step(j, acc=None):
-            solvers[j].solve_host_buffers(init_host, desired_c, out_host[j], res_host[j])
+        def host_begin(j, h):
+            solvers[j][h].solve_host_begin(init_host, desired_c, out_host[j][h], res_host[j][h])
+
+        def host_finish(j, h, acc):
+            solvers[j][h].solve_host_finish()
 
         e2e_steps = max(P, args.steps)
-        run_pipelined(host_step, P)
+        run_pipelined(host_begin, host_finish, P * H)
         barrier()
         t0 = time.perf_counter()
-        run_pipelined(host_step, e2e_steps, stagger_s)
+        run_pipelined(host_begin, host_finish, e2e_steps, stagger_s)
         barrier()
         e2e_t = time.perf_counter() - t0
-        r2 = np.frombuffer(res_host[0].numpy().tobytes(), dtype=RESULT_DTYPE)
+        r2 = np.frombuffer(res_host[0][0].numpy().tobytes(), dtype=RESULT_DTYPE)
         conv2 = int(np.sum((r2["status"] == 1) | (r2["status"] == 2)))
         e2e = {"t": e2e_t, "steps": e2e_steps, "converged": conv2,
                "h2d": B * N * 18 * 8 + N * 18 * 8, "d2h": B * N * 18 * 8 + B * 24}
@@ -387,7 +423,7 @@ def main():
         # the path's one collective: per-problem result records of every shard (24 B/problem) over NCCL
         from quadrotorilqr_b200 import sharding
 
-        allres = sharding.gather_results(dist, res_dev[0].view(B, 24))
+        allres = sharding.gather_results(dist, res_dev[0][0].view(B, 24))
         st_all = np.frombuffer(allres.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)["status"]
         gathered_converged = int(np.sum((st_all == 1) | (st_all == 2)))
     else:
@@ -400,7 +436,7 @@ def main():
     step_ms = max(mx[0], 0.0) / args.steps
     wall_ms = mx[1] / args.steps
     # device events bracket the stream work; the solver also synchronises with the host every
-    # iteration, so the honest per-step time is the larger of the two clocks
+    # super-step, so the honest per-step time is the larger of the two clocks
     ms_per_step = max(step_ms, wall_ms)
     total_converged_per_step = sm[2]
     value = total_converged_per_step / (ms_per_step * 1e-3)
@@ -411,63 +447,80 @@ def main():
     peak = ctypes.c_double(0.0)
     _capi.lib().qilqr_measure_fp64_peak(ctypes.c_int(local_rank), ctypes.byref(peak))
     f_bwd, f_roll, f_cost = VARIANT_FLOPS.get(args.model_variant, (F_BWD, F_ROLL, F_COST))
-    bwd_flops = bwd_knots * f_bwd
-    achieved = bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
-    roll_achieved = roll_knots * (f_roll + f_cost) / (roll_ms * 1e-3) / 1e12 if roll_ms > 0 else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # algorithmic HBM bytes of the backward kernel: read 17 doubles (+17 desired if per-problem), write 52
-    bwd_bytes = bwd_knots * (17 + 52) * 8.0
-    traffic, traffic_note = None, None
+    counters = None
     try:
         if args.model_variant:
-            raise LookupError("no ncu traffic capture is wired in for the model variants")
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        n_bwd_launches = max(1, ser["solver_iterations"])
-        traffic = tj["backward_dram_bytes_per_problem_knot"] * bwd_knots / n_bwd_launches
-        traffic_note = ("dram__bytes_read+write per problem-knot from the committed ncu capture (profiles/r1_traffic.json: "
-                        f"{tj['backward_dram_bytes_per_problem_knot']:.0f} B vs {tj['algorithmic_bytes_per_problem_knot']:.0f} B "
-                        "algorithmic; the difference is the linearisation record round trip) x mean problem-knots per launch")
+            raise LookupError("no ncu capture is wired in for the model variants")
+        counters = json.load(open(os.path.join(ROOT, "profiles", "r2", "r2_kernel_counters.json")))["backward_pass"]
     except Exception:
         pass
+
+    def tflops(knots, flops_per_knot, ms):
+        return knots * flops_per_knot / (ms * 1e-3) / 1e12 if ms > 0 else None
+
+    achieved = tflops(bwd_knots_bulk, f_bwd, bwd_ms_bulk)          # bulk launches: the throughput-bound part
+    achieved_all = tflops(bwd_knots, f_bwd, bwd_ms)                # every launch, the latency-bound tail included
+    exe = counters["executed_flops_per_problem_knot"] if counters else None
+    executed = tflops(bwd_knots_bulk, exe, bwd_ms_bulk) if exe else None
+    n_bulk_steps = n_serial
     roofline = {
         "kernel": ("backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)"
                    if not args.model_variant else
                    "backward pass = k_linearise_dense + k_riccati_dense (model-agnostic ILQR::backwards_pass)"),
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": (achieved / peak.value) if (achieved and peak.value) else None,
+        "frac_definition": "DENSE as-written reference FLOPs (30231 per problem-knot, counted by the oracle's "
+                           "FLOP-counting scalar) / CUDA-event time of the throughput-bound bulk launches / measured "
+                           "DFMA peak; the kernels skip structural zeros, so this mixes 'fewer FLOPs executed' with "
+                           "pipe utilisation -- executed_frac is the utilisation",
+        "executed_tflops": executed,
+        "executed_frac": (executed / peak.value) if (executed and peak.value) else None,
+        "executed_flops_per_problem_knot": exe,
+        "executed_definition": "2*DFMA + DMUL + DADD thread-instructions per problem-knot from the committed ncu capture "
+                               "(profiles/r2/r2_kernel_counters.json: smsp__sass_thread_inst_executed_op_d*_pred_on.sum) x "
+                               "the problem-knots of the bulk launches / their CUDA-event time",
+        "frac_all_launches": (achieved_all / peak.value) if (achieved_all and peak.value) else None,
         "peak_source": "measured in this run: register-resident DFMA kernel (qilqr_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_problem_knot": f_bwd,
-        "flops_definition": "dense as-written reference arithmetic counted by the oracle's FLOP-counting scalar",
-        "traffic": traffic, "traffic_note": traffic_note,
-        "share_of_step": bwd_ms / (serial_ms * n_serial),
-        "timed": f"CUDA events around every launch of {n_serial} un-pipelined steps run right after the timed region",
-        "hbm": {"achieved": bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else None, "peak": hbm_peak,
-                "unit": "GB/s", "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak) if bwd_ms > 0 else None,
+        "traffic": (counters["dram_bytes_per_problem_knot"] * bwd_knots_bulk / max(1, n_bulk_steps)) if counters else None,
+        "traffic_note": ("dram__bytes_read+write per problem-knot from the committed ncu capture x the problem-knots of "
+                         "one step's bulk launches; algorithmic: "
+                         f"{counters['algorithmic_bytes_per_problem_knot']:.0f} B per problem-knot -- the difference is the "
+                         "linearisation record written by k_linearise and read once by k_riccati_g4") if counters else None,
+        "algorithmic_bytes": 552.0 * bwd_knots_bulk / max(1, n_bulk_steps),
+        "timed": (f"CUDA events on the solver's stream around every launch of {n_serial} un-pipelined steps run right "
+                  "after the timed region (kernels of different handles overlap inside it)"),
+        "bulk_ms_per_step": bwd_ms_bulk / n_serial, "all_launches_ms_per_step": bwd_ms / n_serial,
+        "share_of_profiled_step": bwd_ms / (prof_ms * n_serial),
+        "bulk_kernel_ms_vs_ms_per_step": [bwd_ms_bulk / n_serial, ms_per_step],
+        "hbm": {"achieved": (bwd_knots_bulk * (17 + 52) * 8.0) / (bwd_ms_bulk * 1e-3) / 1e9 if bwd_ms_bulk > 0 else None,
+                "peak": hbm_peak, "unit": "GB/s",
+                "frac": ((bwd_knots_bulk * (17 + 52) * 8.0) / (bwd_ms_bulk * 1e-3) / 1e9 / hbm_peak) if bwd_ms_bulk > 0 else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "of fallback"},
-        "rollout_kernel": {"achieved": roll_achieved, "unit": "TFLOP/s", "share_of_step": roll_ms / (serial_ms * n_serial)},
+        "rollout_kernel": {"achieved": tflops(roll_knots, f_roll + f_cost, roll_ms), "unit": "TFLOP/s",
+                           "share_of_profiled_step": roll_ms / (prof_ms * n_serial)},
     }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batch {B} hover problems/GPU, N={N}, dt=0.1, reference default options "
-                               "(rtol=atol=1e-12, max_iters=100, line search 0.5/0.5/100), "
-                               "torque_to_thrust_ratio=0.1, x0: pos U[-1,1]^3, angle U[0,0.5] rad, vel U[-0.25,0.25]^6 "
-                               f"(Philox seed {args.seed})",
+        "config": {"workload": workload_string(B, args.seed),
                    "cache": "inputs larger than L2 (356 MB trajectories + 1.4 GB gains per step vs 126 MB L2)",
                    "parallelism": f"{world} independent shard(s), one process per GPU",
                    **({"model_variant": f"{args.model_variant} (NOT the BASELINE model: see --model-variant)"}
                       if args.model_variant else {}),
-                   "pipeline": f"{P} batches in flight per GPU (one solver handle + host thread + stream pair each, "
-                               f"CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')}), "
-                               f"started {1e3 * stagger_s:.1f} ms apart; each step is one full batch"},
+                   "pipeline": f"{P} batches in flight per GPU ({P} host threads x {H} solver handle(s), each on its own "
+                               "stream pair), "
+                               f"CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')}, "
+                               f"threads started {1e3 * stagger_s:.1f} ms apart; each step is one full batch"},
         "serial_ms_per_step": serial_ms,
         "serial_value": (converged / (serial_ms * 1e-3)) if serial_ms else None,
         "us_per_iteration": us_per_iter,
@@ -490,7 +543,8 @@ def main():
         line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * mx[7] / e2e["steps"],
                        "steps": e2e["steps"],
-                       "api": "qilqr_solve_host (pinned host AoS in/out, results struct per problem)"}
+                       "api": "qilqr_solve_host_begin / _finish (pinned host AoS in/out, results struct per problem; "
+                              "same results as qilqr_solve_host)"}
     if not args.no_cpu_baseline and world >= 1:
         import oracle as O
 

@@ -149,6 +149,16 @@ int qilqr_solve_host(qilqr_solver_t *solver, int batch, int n_knots, const doubl
                      double *out_K, double *cost_hist, int hist_cap, double *debug_traj,
                      int debug_cap, qilqr_result_t *results);
 
+/* The same solve in two halves, for callers that keep several batches in flight.  qilqr_solve_host_begin
+ * returns as soon as the host has nothing left to sequence: the upload, the throughput-bound part of the solve
+ * and the hand-over of the last few problems (the ones that creep to max_iters) to a kernel that finishes them on
+ * its own.  qilqr_solve_host_finish waits for that kernel and copies trajectories and results back.  Between the
+ * two calls the handle accepts no other call; run the next batch on another handle meanwhile.  out_traj and
+ * results must stay valid until _finish returns.  Same results as qilqr_solve_host, bit for bit. */
+int qilqr_solve_host_begin(qilqr_solver_t *solver, int batch, int n_knots, const double *desired, int desired_count,
+                           const double *initial, double *out_traj, qilqr_result_t *results);
+int qilqr_solve_host_finish(qilqr_solver_t *solver);
+
 /* ILQR::forward_sim (ilqr.hh:149-172): alpha [batch]. */
 int qilqr_forward_sim_host(qilqr_solver_t *solver, int batch, int n_knots, const double *current,
                            const double *k, const double *K, const double *alpha, double *out_traj);
@@ -203,6 +213,13 @@ int qilqr_cost_host(qilqr_solver_t *solver, int batch, const double *x, const do
 int qilqr_solve_device(qilqr_solver_t *solver, int batch, int n_knots, const double *d_desired,
                        int desired_count, double *d_traj_inout, double *d_k, double *d_K,
                        double *d_cost_hist, int hist_cap, qilqr_result_t *d_results);
+/* qilqr_solve_device in two halves (see qilqr_solve_host_begin): _begin returns once the device finishes the solve
+ * on its own, _finish waits and completes d_traj_inout / d_results.  The buffers passed to _begin must not be
+ * touched in between. */
+int qilqr_solve_device_begin(qilqr_solver_t *solver, int batch, int n_knots, const double *d_desired,
+                             int desired_count, double *d_traj_inout, double *d_k, double *d_K,
+                             double *d_cost_hist, int hist_cap, qilqr_result_t *d_results);
+int qilqr_solve_device_finish(qilqr_solver_t *solver);
 /* AoS <-> SoA transposition kernels (device to device). */
 int qilqr_pack_trajectory_device(qilqr_solver_t *solver, int batch, int n_knots,
                                  const double *d_aos /*[batch][n][18]*/, double *d_soa);
@@ -244,6 +261,12 @@ typedef struct {
   int64_t rollout_problem_knots;  /* problem-knots processed by rollout kernels */
   double bulk_wall_ms;            /* host wall time of the solve loop while more than hi_threshold problems were active */
   double tail_wall_ms;            /* ... and after the switch to the high-priority tail stream */
+  /* the part of backward_ms / rollout_ms / backward_problem_knots spent in launches of the throughput-bound bulk
+   * (more than `hi_threshold` problems alive); the rest is the latency-bound tail of the few problems that creep to
+   * max_iters */
+  double backward_ms_bulk;
+  double rollout_ms_bulk;
+  int64_t backward_problem_knots_bulk;
 } qilqr_solve_stats_t;
 int qilqr_last_solve_stats(const qilqr_solver_t *solver, qilqr_solve_stats_t *out);
 /* Enable/disable per-kernel CUDA-event timing (adds a few microseconds per launch). */

@@ -77,6 +77,9 @@ class SolveStats(C.Structure):
         ("rollout_problem_knots", C.c_int64),
         ("bulk_wall_ms", C.c_double),
         ("tail_wall_ms", C.c_double),
+        ("backward_ms_bulk", C.c_double),
+        ("rollout_ms_bulk", C.c_double),
+        ("backward_problem_knots_bulk", C.c_int64),
     ]
 
 
@@ -91,7 +94,8 @@ EXPORTED_SYMBOLS = [
     "qilqr_unpack_trajectory_device", "qilqr_rollout_constant_control_device",
     "qilqr_last_solve_stats", "qilqr_set_profiling", "qilqr_measure_fp64_peak",
     "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
-    "qilqr_set_model_variant", "qilqr_build_info",
+    "qilqr_set_model_variant", "qilqr_build_info", "qilqr_solve_host_begin", "qilqr_solve_host_finish",
+    "qilqr_solve_device_begin", "qilqr_solve_device_finish",
 ]
 
 MODEL_REFERENCE = 0

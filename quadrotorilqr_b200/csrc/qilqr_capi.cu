@@ -51,7 +51,8 @@ struct DeviceBuffer {
 
 struct TimedSpan {
   cudaEvent_t start, stop;
-  int kind;  // 0 backward, 1 rollout
+  int kind;   // 0 backward, 1 rollout
+  bool bulk;  // launched while the solve was in its throughput-bound bulk (more than hi_threshold problems alive)
 };
 
 }  // namespace
@@ -68,6 +69,12 @@ struct SolveCtx {  // what a solve leaves pending when its tail runs on the devi
   std::chrono::steady_clock::time_point t_begin, t_switch;
 };
 
+struct HostCall {  // where the results of a host-buffer solve go (qilqr_solve_host / _begin / _finish)
+  bool pending = false;
+  int B = 0, N = 0, hist_cap = 0, debug_cap = 0;
+  double *out_traj = nullptr, *out_k = nullptr, *out_K = nullptr, *cost_hist = nullptr, *debug_traj = nullptr;
+  qilqr_result_t *results = nullptr;
+};
 }  // namespace
 
 struct qilqr_solver {
@@ -81,7 +88,9 @@ struct qilqr_solver {
   int seq = 0;                       // sequence number of the last compaction (see wait_counts)
   int lists_B = 0;                   // batch the list buffer is laid out for
   int hi_threshold = 2048;           // switch to stream_hi when at most this many problems are active
-  int bulk_poll_us = 0;              // QILQR_BULK_POLL_US: sleep this long between polls while on the bulk stream (0: spin)
+  int bulk_poll_us = 20;             // QILQR_BULK_POLL_US: sleep this long between polls of the list lengths while the
+                                     // solve is in its bulk (the kernels ahead take milliseconds); 0: spin.  Keeps the host
+                                     // threads of many pipelined handles / ranks from needing a core each.
   bool tail_stream = true;           // QILQR_TAIL_STREAM=0: the tail stays on the handle's main stream (one stream per handle)
   bool in_tail = false;              // the current solve has entered its latency-bound tail
   std::string last_error;
@@ -104,13 +113,14 @@ struct qilqr_solver {
   // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
   DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map, tail_lists, rec_tail_d;
   bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
-  bool persistent_tail = true;  // QILQR_PERSISTENT_TAIL=0: keep the host-driven loop to the end
-  int persist_threshold = 64;   // ... one kernel finishes the solve once at most this many problems are alive
+  bool persistent_tail = false;  // QILQR_PERSISTENT_TAIL=1: one kernel finishes the solve on the device once at most
+  int persist_threshold = 64;    // `persist_threshold` problems are alive (frees the host thread: begin / finish API)
   int always_hist_cap = 128;    // per-problem cost history kept on the device even when the caller passes no buffer
   int *h_counts = nullptr;  // mapped pinned: [0] = alive, [1] = active, [2] = sequence number of the compaction
   int *d_counts = nullptr;
   long long *h_totals = nullptr;  // pinned: sums over the batch of backward passes and rollouts of the last solve
   SolveCtx ctx;                   // a solve whose tail is still running on the device (begin / finish API)
+  HostCall host_call;
   std::mutex mu;                  // one call at a time per handle (the workspace is shared by every entry point)
 };
 
@@ -129,6 +139,13 @@ int fail(qilqr_solver *S, int code, const char *msg) {
   if (S) S->last_error = msg;
   return code;
 }
+// Every entry point that touches the handle's workspace: one call at a time per handle (the reference's solver
+// methods are const and re-entrant; here the workspace is shared, so concurrent callers are serialised), and
+// nothing may run between ..._begin and ..._finish.
+#define QENTER(S)                                                                                          \
+  std::lock_guard<std::mutex> lock__((S)->mu);                                                             \
+  if ((S)->ctx.pending || (S)->host_call.pending)                                                          \
+    return fail((S), QILQR_ERR_INVALID_ARGUMENT, "a solve begun with qilqr_solve_*_begin is still pending on this handle")
 
 cudaEvent_t get_event(qilqr_solver *S) {
   if (!S->event_pool.empty()) {
@@ -149,6 +166,7 @@ struct SpanGuard {
       sp.start = get_event(S);
       sp.stop = get_event(S);
       sp.kind = kind;
+      sp.bulk = !S->in_tail;
       cudaEventRecord(sp.start, S->cur);
     }
   }
@@ -164,6 +182,7 @@ void drain_spans(qilqr_solver *S) {  // call after a stream synchronise
     float ms = 0.f;
     cudaEventElapsedTime(&ms, sp.start, sp.stop);
     (sp.kind == 0 ? S->stats.backward_ms : S->stats.rollout_ms) += ms;
+    if (sp.bulk) (sp.kind == 0 ? S->stats.backward_ms_bulk : S->stats.rollout_ms_bulk) += ms;
     S->event_pool.push_back(sp.start);
     S->event_pool.push_back(sp.stop);
   }
@@ -511,6 +530,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         if ((rc = launch_backward(S, ba))) return rc;
       }
       S->stats.backward_problem_knots += int64_t(n_active) * N;
+      if (!S->in_tail) S->stats.backward_problem_knots_bulk += int64_t(n_active) * N;
       ++S->launches;
     }
     if (P_alpha > 1 && epoch > 0) {
@@ -789,17 +809,33 @@ int qilqr_solve_device(qilqr_solver_t *S, int batch, int n_knots, const double *
                        double *d_traj_inout, double *d_k, double *d_K, double *d_cost_hist, int hist_cap,
                        qilqr_result_t *d_results) {
   if (!S || !d_desired || !d_traj_inout) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
   return solve_core(S, batch, n_knots, d_desired, desired_count, d_traj_inout, d_k, d_K, d_cost_hist, hist_cap,
                     d_results, nullptr, 0);
 }
+int qilqr_solve_device_begin(qilqr_solver_t *S, int batch, int n_knots, const double *d_desired, int desired_count,
+                             double *d_traj_inout, double *d_k, double *d_K, double *d_cost_hist, int hist_cap,
+                             qilqr_result_t *d_results) {
+  if (!S || !d_desired || !d_traj_inout) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  return solve_core(S, batch, n_knots, d_desired, desired_count, d_traj_inout, d_k, d_K, d_cost_hist, hist_cap,
+                    d_results, nullptr, 0, /*async_tail=*/true);
+}
+int qilqr_solve_device_finish(qilqr_solver_t *S) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  return solve_finish(S, S->ctx);
+}
 int qilqr_pack_trajectory_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_aos, double *d_soa) {
   if (!S || !d_aos || !d_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   return pack_traj(S, batch, n_knots, d_aos, d_soa);
 }
 int qilqr_unpack_trajectory_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_soa,
                                    const double *d_time_aos, double *d_aos) {
   if (!S || !d_aos || !d_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   const size_t bytes = sizeof(double) * size_t(batch) * n_knots * 18;
   if (d_time_aos && d_time_aos != d_aos)
@@ -811,6 +847,7 @@ int qilqr_unpack_trajectory_device(qilqr_solver_t *S, int batch, int n_knots, co
 int qilqr_rollout_constant_control_device(qilqr_solver_t *S, int batch, int n_knots, const double *d_x0_soa,
                                           const double *u, double *d_traj_soa) {
   if (!S || !d_x0_soa || !u || !d_traj_soa) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   k_rollout_constant<<<blocks_for(batch, 128), 128, 0, S->stream>>>(S->p, d_x0_soa, u[0], u[1], u[2], u[3],
                                                                    d_traj_soa, batch, n_knots);
@@ -822,6 +859,7 @@ int qilqr_rollout_constant_control_device(qilqr_solver_t *S, int batch, int n_kn
 int qilqr_mpc_advance_device(qilqr_solver_t *S, int B, int N, double *d_traj, double *d_plant, const double *d_dist,
                              double *d_applied_u) {
   if (!S || !d_traj || !d_plant || B <= 0 || N <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   k_mpc_advance<<<blocks_for(B, 128), 128, 0, S->stream>>>(S->p, d_traj, d_plant, d_dist, d_applied_u, B, N);
   ++S->launches;
@@ -833,6 +871,7 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
                          double *d_plant, const double *d_dist, double *d_state_log, double *d_control_log,
                          int64_t *totals) {
   if (!S || !d_desired || !d_traj || !d_plant || steps < 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
   std::vector<qilqr_result_t> res(totals ? B : 0);
@@ -850,6 +889,9 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
     total_stats.rollout_ms += S->stats.rollout_ms;
     total_stats.backward_problem_knots += S->stats.backward_problem_knots;
     total_stats.rollout_problem_knots += S->stats.rollout_problem_knots;
+    total_stats.backward_ms_bulk += S->stats.backward_ms_bulk;
+    total_stats.rollout_ms_bulk += S->stats.rollout_ms_bulk;
+    total_stats.backward_problem_knots_bulk += S->stats.backward_problem_knots_bulk;
     total_stats.bulk_wall_ms += S->stats.bulk_wall_ms;
     total_stats.tail_wall_ms += S->stats.tail_wall_ms;
     double *u_log = d_control_log ? d_control_log + size_t(t) * 4 * B : nullptr;
@@ -878,14 +920,72 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
 }
 
 // ---- host-buffer API -----------------------------------------------------------
-int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *initial,
+namespace {
+// Second half of qilqr_solve_host: wait for the solve, bring the results back in the caller's layout.
+int solve_host_finish(qilqr_solver *S) {
+  HostCall &hc = S->host_call;
+  if (!hc.pending) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "no host solve is pending");
+  hc.pending = false;
+  int rc = solve_finish(S, S->ctx);
+  if (rc) return rc;
+  cudaStream_t st_ = S->stream;
+  const int B = hc.B, N = hc.N;
+  const size_t traj_bytes = sizeof(double) * size_t(B) * N * 18;
+  // results back: stage_a still holds the input AoS (time_s column), unpack over it
+  unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
+  QCUDA(S, cudaMemcpyAsync(hc.out_traj, S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+  if (hc.results) QCUDA(S, cudaMemcpyAsync(hc.results, S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost, st_));
+  if (hc.out_k) {
+    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+    transpose_to_aos(S, S->gk.as<double>(), S->stage_c.as<double>(), B, N, 4);
+    QCUDA(S, cudaMemcpyAsync(hc.out_k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
+  }
+  if (hc.out_K) {
+    if (hc.out_k) QCUDA(S, cudaStreamSynchronize(st_));  // stage_c is reused
+    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
+    transpose_to_aos(S, S->gK.as<double>(), S->stage_c.as<double>(), B, N, 48);
+    QCUDA(S, cudaMemcpyAsync(hc.out_K, S->stage_c.ptr, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyDeviceToHost, st_));
+  }
+  if (hc.cost_hist) {  // [hist_cap][B] -> [B][hist_cap]
+    QCUDA(S, S->stage_b.ensure(sizeof(double) * size_t(hc.hist_cap) * B));
+    transpose_to_aos(S, S->hist_d.as<double>(), S->stage_b.as<double>(), B, 1, hc.hist_cap);
+    QCUDA(S, cudaMemcpyAsync(hc.cost_hist, S->stage_b.ptr, sizeof(double) * size_t(hc.hist_cap) * B, cudaMemcpyDeviceToHost, st_));
+  }
+  QCUDA(S, cudaStreamSynchronize(st_));
+  if (hc.debug_traj) {
+    // [cap][N][17][B] on the device -> [B][cap][N][18] on the host, one slot at a time
+    double *d_debug = S->debug_d.as<double>();
+    std::vector<qilqr_result_t> res(B);
+    QCUDA(S, cudaMemcpy(res.data(), S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost));
+    int max_nd = 0;
+    for (int b = 0; b < B; ++b) max_nd = std::max(max_nd, res[b].num_debug);
+    max_nd = std::min(max_nd, hc.debug_cap);
+    std::vector<double> slot(size_t(B) * N * 18);
+    for (int sidx = 0; sidx < max_nd; ++sidx) {
+      // stage_a still has time_s in column 0
+      unpack_traj(S, B, N, d_debug + size_t(sidx) * N * 17 * B, S->stage_a.as<double>());
+      QCUDA(S, cudaMemcpyAsync(slot.data(), S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+      QCUDA(S, cudaStreamSynchronize(st_));
+      for (int b = 0; b < B; ++b)
+        if (sidx < res[b].num_debug)
+          std::memcpy(hc.debug_traj + (size_t(b) * hc.debug_cap + sidx) * N * 18, slot.data() + size_t(b) * N * 18,
+                      sizeof(double) * N * 18);
+    }
+  }
+  QCUDA(S, cudaGetLastError());
+  return QILQR_OK;
+}
+
+// First half: upload, transpose to structure-of-arrays, sequence the solve (all of it, or -- async -- up to the
+// point where the device finishes it on its own).
+int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int Bd, const double *initial,
                      double *out_traj, double *out_k, double *out_K, double *cost_hist, int hist_cap,
-                     double *debug_traj, int debug_cap, qilqr_result_t *results) {
+                     double *debug_traj, int debug_cap, qilqr_result_t *results, bool async) {
   if (!S || !desired || !initial || !out_traj) return QILQR_ERR_INVALID_ARGUMENT;
   if (B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "bad batch/knots/desired_count");
+  if (S->ctx.pending || S->host_call.pending) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "a solve is still pending on this handle");
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
-  const size_t traj_bytes = sizeof(double) * size_t(B) * N * 18;
   QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
   QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(N) * 17 * Bd));
   int rc = upload_traj(S, S->stage_b, Bd, N, desired, S->desired_soa.as<double>());
@@ -902,60 +1002,56 @@ int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int
   }
   const bool want_debug = debug_traj && debug_cap > 0 && S->opt.populate_debug;
   if (want_debug) {
-    QCUDA(S, S->debug_d.ensure(sizeof(double) * size_t(debug_cap) * N * 17 * B));
+    const size_t need = sizeof(double) * size_t(debug_cap) * N * 17 * B;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (need > S->debug_d.bytes && need > free_b)
+      return fail(S, QILQR_ERR_OUT_OF_MEMORY, "the ILQRDebug capture of every problem does not fit in device memory: sample "
+                                               "problems with qilqr_set_debug_sampling or solve in smaller batches");
+    QCUDA(S, S->debug_d.ensure(need));
     d_debug = S->debug_d.as<double>();
-    QCUDA(S, cudaMemsetAsync(d_debug, 0, sizeof(double) * size_t(debug_cap) * N * 17 * B, st_));  // slots a problem never reaches
+    QCUDA(S, cudaMemsetAsync(d_debug, 0, need, st_));  // slots a problem never reaches
   }
   QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
+  HostCall &hc = S->host_call;
+  hc = HostCall{};
+  hc.B = B; hc.N = N;
+  hc.out_traj = out_traj; hc.out_k = out_k; hc.out_K = out_K;
+  hc.cost_hist = d_hist ? cost_hist : nullptr; hc.hist_cap = hist_cap;
+  hc.debug_traj = want_debug ? debug_traj : nullptr; hc.debug_cap = debug_cap;
+  hc.results = results;
   rc = solve_core(S, B, N, S->desired_soa.as<double>(), Bd, S->traj_soa.as<double>(), d_k, d_K, d_hist, hist_cap,
-                  S->results_d.as<qilqr_result_t>(), d_debug, debug_cap);
+                  S->results_d.as<qilqr_result_t>(), d_debug, debug_cap, /*async_tail=*/true);
   if (rc) return rc;
-  // results back: stage_a still holds the input AoS (time_s column), unpack over it
-  unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
-  QCUDA(S, cudaMemcpyAsync(out_traj, S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
-  if (results) QCUDA(S, cudaMemcpyAsync(results, S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost, st_));
-  if (out_k) {
-    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
-    transpose_to_aos(S, d_k, S->stage_c.as<double>(), B, N, 4);
-    QCUDA(S, cudaMemcpyAsync(out_k, S->stage_c.ptr, sizeof(double) * size_t(N) * 4 * B, cudaMemcpyDeviceToHost, st_));
-  }
-  if (out_K) {
-    QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
-    transpose_to_aos(S, d_K, S->stage_c.as<double>(), B, N, 48);
-    QCUDA(S, cudaMemcpyAsync(out_K, S->stage_c.ptr, sizeof(double) * size_t(N) * 48 * B, cudaMemcpyDeviceToHost, st_));
-  }
-  if (d_hist) {  // [hist_cap][B] -> [B][hist_cap]
-    QCUDA(S, S->stage_b.ensure(sizeof(double) * size_t(hist_cap) * B));
-    transpose_to_aos(S, d_hist, S->stage_b.as<double>(), B, 1, hist_cap);
-    QCUDA(S, cudaMemcpyAsync(cost_hist, S->stage_b.ptr, sizeof(double) * size_t(hist_cap) * B, cudaMemcpyDeviceToHost, st_));
-  }
-  QCUDA(S, cudaStreamSynchronize(st_));
-  if (want_debug) {
-    // [cap][N][17][B] on the device -> [B][cap][N][18] on the host, one slot at a time
-    std::vector<qilqr_result_t> res(B);
-    QCUDA(S, cudaMemcpy(res.data(), S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost));
-    int max_nd = 0;
-    for (int b = 0; b < B; ++b) max_nd = std::max(max_nd, res[b].num_debug);
-    max_nd = std::min(max_nd, debug_cap);
-    std::vector<double> slot(size_t(B) * N * 18);
-    for (int sidx = 0; sidx < max_nd; ++sidx) {
-      // stage_a still has time_s in column 0
-      unpack_traj(S, B, N, d_debug + size_t(sidx) * N * 17 * B, S->stage_a.as<double>());
-      QCUDA(S, cudaMemcpyAsync(slot.data(), S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
-      QCUDA(S, cudaStreamSynchronize(st_));
-      for (int b = 0; b < B; ++b)
-        if (sidx < res[b].num_debug)
-          std::memcpy(debug_traj + (size_t(b) * debug_cap + sidx) * N * 18, slot.data() + size_t(b) * N * 18,
-                      sizeof(double) * N * 18);
-    }
-  }
-  QCUDA(S, cudaGetLastError());
-  return QILQR_OK;
+  hc.pending = true;
+  return async ? QILQR_OK : solve_host_finish(S);
+}
+}  // namespace
+
+int qilqr_solve_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *initial,
+                     double *out_traj, double *out_k, double *out_K, double *cost_hist, int hist_cap,
+                     double *debug_traj, int debug_cap, qilqr_result_t *results) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  return solve_host_begin(S, B, N, desired, Bd, initial, out_traj, out_k, out_K, cost_hist, hist_cap, debug_traj,
+                          debug_cap, results, false);
+}
+int qilqr_solve_host_begin(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *initial,
+                           double *out_traj, qilqr_result_t *results) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  return solve_host_begin(S, B, N, desired, Bd, initial, out_traj, nullptr, nullptr, nullptr, 0, nullptr, 0, results, true);
+}
+int qilqr_solve_host_finish(qilqr_solver_t *S) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  return solve_host_finish(S);
 }
 
 int qilqr_forward_sim_host(qilqr_solver_t *S, int B, int N, const double *current, const double *k, const double *K,
                            const double *alpha, double *out_traj) {
   if (!S || !current || !k || !K || !alpha || !out_traj || B <= 0 || N <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
   QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
@@ -988,6 +1084,7 @@ int qilqr_cost_trajectory_host(qilqr_solver_t *S, int B, int N, const double *de
                                const double *traj, double *cost) {
   if (!S || !desired || !traj || !cost || B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return QILQR_ERR_INVALID_ARGUMENT;
   if (n_desired < N) return fail(S, QILQR_ERR_OUT_OF_RANGE, "vector::_M_range_check (cost.hh:39-40)");
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
   QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
@@ -1010,6 +1107,7 @@ int qilqr_backwards_pass_host(qilqr_solver_t *S, int B, int N, const double *des
                               double *k, double *K, double *terms) {
   if (!S || !desired || !traj || !k || !K || !terms || B <= 0 || N <= 0 || (Bd != 1 && Bd != B))
     return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
   QCUDA(S, S->traj_soa.ensure(sizeof(double) * size_t(N) * 17 * B));
@@ -1043,6 +1141,7 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
   if (!S || !desired || !current || !current_cost || !k || !K || !terms || !out_traj || !new_cost || !step ||
       !status || B <= 0 || N <= 0 || (Bd != 1 && Bd != B))
     return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
   int rc = ensure_state(S, B);
@@ -1138,6 +1237,7 @@ int fetch(qilqr_solver *S, double *h, const double *d, size_t n) {
 int qilqr_discrete_dynamics_host(qilqr_solver_t *S, int B, const double *x, const double *u, double *x_next,
                                  double *J_x, double *J_u) {
   if (!S || !x || !u || !x_next || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   int rc = 0;
   Staged sg;
@@ -1157,6 +1257,7 @@ int qilqr_discrete_dynamics_host(qilqr_solver_t *S, int B, const double *x, cons
 int qilqr_continuous_dynamics_host(qilqr_solver_t *S, int B, const double *x, const double *u, double *xdot,
                                    double *J_x, double *J_u) {
   if (!S || !x || !u || !xdot || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   int rc = 0;
   Staged sg;
@@ -1176,6 +1277,7 @@ int qilqr_continuous_dynamics_host(qilqr_solver_t *S, int B, const double *x, co
 int qilqr_state_minus_host(qilqr_solver_t *S, int B, const double *lhs, const double *rhs, double *out, double *J_lhs,
                            double *J_rhs) {
   if (!S || !lhs || !rhs || !out || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   int rc = 0;
   Staged sg;
@@ -1195,6 +1297,7 @@ int qilqr_state_minus_host(qilqr_solver_t *S, int B, const double *lhs, const do
 int qilqr_state_add_host(qilqr_solver_t *S, int B, const double *x, const double *tangent, double *out, double *J_lhs,
                          double *J_rhs) {
   if (!S || !x || !tangent || !out || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   int rc = 0;
   Staged sg;
@@ -1214,6 +1317,7 @@ int qilqr_state_add_host(qilqr_solver_t *S, int B, const double *x, const double
 int qilqr_cost_host(qilqr_solver_t *S, int B, const double *x, const double *u, const double *x_d, const double *u_d,
                     double *cost, double *C_x, double *C_u, double *C_xx, double *C_uu, double *C_xu) {
   if (!S || !x || !u || !x_d || !u_d || !cost || B <= 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
   QCUDA(S, cudaSetDevice(S->device));
   int rc = 0;
   Staged sg;

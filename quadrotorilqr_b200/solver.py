@@ -149,11 +149,22 @@ class BatchILQR:
         B, N, _ = initial.shape
         desired = _f64(desired)
         Bd = 1 if desired.ndim == 2 else desired.shape[0]
+        if out is not None and not (isinstance(out, np.ndarray) and out.dtype == np.float64
+                                    and out.shape == (B, N, 18) and out.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"out must be a C-contiguous float64 array of shape {(B, N, 18)}")
         traj = out if out is not None else np.empty((B, N, 18))
         k = np.empty((B, N, 4)) if want_gains else None
         K = np.empty((B, N, 4, 12)) if want_gains else None
         hist = np.zeros((B, hist_cap)) if hist_cap else None
-        dbg_cap = int(np.ceil(self.options.convergence_criteria.max_iters)) if want_debug else 0
+        max_iters = self.options.convergence_criteria.max_iters
+        dbg_cap = 0
+        if want_debug:  # ILQRDebug of every problem: one trajectory per completed iteration (ilqr_debug.hh:9-22)
+            dbg_cap = int(np.ceil(max_iters)) if np.isfinite(max_iters) and max_iters > 0 else 0
+            if B * dbg_cap * N * 18 * 8 > self.MAX_DEBUG_BYTES:
+                raise ValueError(
+                    f"populate_debug for {B} problems x {dbg_cap} iterations x {N} knots needs "
+                    f"{B * dbg_cap * N * 144 / 2**30:.1f} GiB; sample problems / iterations with solve_sampled_debug(), "
+                    "solve a smaller batch, or lower convergence_criteria.max_iters")
         dbg = np.zeros((B, dbg_cap, N, 18)) if dbg_cap else None
         res = np.zeros(B, dtype=RESULT_DTYPE)
         rc = _capi.lib().qilqr_solve_host(self._h, C.c_int(B), C.c_int(N), _ptr(desired), C.c_int(Bd),
@@ -161,6 +172,32 @@ class BatchILQR:
                                           C.c_int(hist_cap), _ptr(dbg), C.c_int(dbg_cap), _ptr(res))
         self._check(rc)
         return dict(traj=traj, results=res, k=k, K=K, cost_history=hist, debug=dbg)
+
+    MAX_DEBUG_BYTES = 8 << 30  # refuse to stage more than this for a full ILQRDebug capture
+
+    def solve_host_begin(self, initial, desired, out_traj, results):
+        """First half of :meth:`solve_host_buffers` (``qilqr_solve_host_begin``): returns once the device finishes the
+        batch on its own; call :meth:`solve_host_finish` before touching ``out_traj`` / ``results``."""
+        B, N = int(initial.shape[0]), int(initial.shape[1])
+        Bd = 1 if desired.ndim == 2 else int(desired.shape[0])
+        self._check(_capi.lib().qilqr_solve_host_begin(self._h, C.c_int(B), C.c_int(N), _ptr(desired), C.c_int(Bd),
+                                                       _ptr(initial), _ptr(out_traj), _ptr(results)))
+
+    def solve_host_finish(self):
+        self._check(_capi.lib().qilqr_solve_host_finish(self._h))
+
+    def solve_device_begin(self, traj_soa, desired_soa, results=None, k=None, K=None, cost_hist=None):
+        """First half of :meth:`solve_device` (``qilqr_solve_device_begin``)."""
+        N, rows, B = traj_soa.shape
+        assert rows == 17 and desired_soa.shape[0] == N and desired_soa.shape[1] == 17
+        Bd = int(desired_soa.shape[2])
+        hist_cap = int(cost_hist.shape[0]) if cost_hist is not None else 0
+        self._check(_capi.lib().qilqr_solve_device_begin(self._h, C.c_int(B), C.c_int(N), _ptr(desired_soa),
+                                                         C.c_int(Bd), _ptr(traj_soa), _ptr(k), _ptr(K),
+                                                         _ptr(cost_hist), C.c_int(hist_cap), _ptr(results)))
+
+    def solve_device_finish(self):
+        self._check(_capi.lib().qilqr_solve_device_finish(self._h))
 
     def solve_host_buffers(self, initial, desired, out_traj, results):
         """Zero-allocation variant for (pinned) host buffers: numpy arrays or CPU torch tensors."""
