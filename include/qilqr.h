@@ -159,6 +159,30 @@ int qilqr_solve_host_begin(qilqr_solver_t *solver, int batch, int n_knots, const
                            const double *initial, double *out_traj, qilqr_result_t *results);
 int qilqr_solve_host_finish(qilqr_solver_t *solver);
 
+/* ---------------------------------------------------------------------------
+ * ILQRDebug at batch scale (ilqr.hh:78-80, ilqr_debug.hh:9-22, ilqr_debug.proto:7-14).  A full capture is
+ * iterations x n_knots x 144 bytes per problem (35 GB for 65536 problems): qilqr_solve_host's debug_traj argument
+ * is meant for single problems and small batches.  For large batches:
+ *
+ *   - the per-iteration COST of every problem is always kept on the device (8 bytes per completed iteration, up to
+ *     128 iterations; QILQR_ALWAYS_HIST_CAP) and read back on demand with qilqr_last_cost_history_host:
+ *     out [count][out_cap] for problems first .. first+count-1 of the last solve, zero-padded; *stored_cap = entries
+ *     kept per problem (a problem's valid entries: results[b].num_debug);
+ *   - TRAJECTORIES are captured for a sample only: qilqr_set_debug_sampling selects the problems (indices into the
+ *     batch, any order) and the iterations (i % every_kth_iteration == 0), kept in a ring of `ring_slots` slots
+ *     per sampled problem (the last ring_slots sampled iterations survive).  With options.populate_debug set, every
+ *     following solve fills the rings; qilqr_read_debug_samples_host copies them back in one asynchronous transfer
+ *     per array (pass pinned memory): traj [S][ring_slots][n_knots][18], iters [S][ring_slots] (iteration index of a
+ *     slot, -1 = empty), costs [S][ring_slots] (new_cost of that iteration), counts [S] (sampled iterations seen;
+ *     slot of the j-th one = j % ring_slots).  num_problems = 0 switches sampling off.
+ * ------------------------------------------------------------------------- */
+int qilqr_set_debug_sampling(qilqr_solver_t *solver, int every_kth_iteration, const int32_t *problems,
+                             int num_problems, int ring_slots);
+int qilqr_read_debug_samples_host(qilqr_solver_t *solver, double *traj, int32_t *iters, double *costs,
+                                  int32_t *counts);
+int qilqr_last_cost_history_host(qilqr_solver_t *solver, int first, int count, double *out, int out_cap,
+                                 int *stored_cap);
+
 /* ILQR::forward_sim (ilqr.hh:149-172): alpha [batch]. */
 int qilqr_forward_sim_host(qilqr_solver_t *solver, int batch, int n_knots, const double *current,
                            const double *k, const double *K, const double *alpha, double *out_traj);

@@ -95,7 +95,8 @@ EXPORTED_SYMBOLS = [
     "qilqr_last_solve_stats", "qilqr_set_profiling", "qilqr_measure_fp64_peak",
     "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
     "qilqr_set_model_variant", "qilqr_build_info", "qilqr_solve_host_begin", "qilqr_solve_host_finish",
-    "qilqr_solve_device_begin", "qilqr_solve_device_finish",
+    "qilqr_solve_device_begin", "qilqr_solve_device_finish", "qilqr_set_debug_sampling",
+    "qilqr_read_debug_samples_host", "qilqr_last_cost_history_host",
 ]
 
 MODEL_REFERENCE = 0

@@ -116,9 +116,15 @@ struct qilqr_solver {
   bool persistent_tail = false;  // QILQR_PERSISTENT_TAIL=1: one kernel finishes the solve on the device once at most
   int persist_threshold = 64;    // `persist_threshold` problems are alive (frees the host thread: begin / finish API)
   int always_hist_cap = 128;    // per-problem cost history kept on the device even when the caller passes no buffer
+  int last_hist_cap = 0, last_hist_B = 0;  // ... of the last solve (qilqr_last_cost_history_host)
+  bool last_hist_internal = false;
   int *h_counts = nullptr;  // mapped pinned: [0] = alive, [1] = active, [2] = sequence number of the compaction
   int *d_counts = nullptr;
   long long *h_totals = nullptr;  // pinned: sums over the batch of backward passes and rollouts of the last solve
+  // sampled ILQRDebug stream (qilqr_set_debug_sampling): which problems / iterations, and the device ring buffers
+  DeviceBuffer dbg_sample, dbg_traj, dbg_iters, dbg_costs, dbg_count;
+  int dbg_S = 0, dbg_ring = 0, dbg_every = 0, dbg_N = 0;  // dbg_S == 0: sampling off; dbg_N: knots of the captured solve
+  const double *dbg_time_aos = nullptr;                    // host path: the input AoS on the device (time_s column)
   SolveCtx ctx;                   // a solve whose tail is still running on the device (begin / finish API)
   HostCall host_call;
   std::mutex mu;                  // one call at a time per handle (the workspace is shared by every entry point)
@@ -425,11 +431,17 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B));
     d_K = S->gK.as<double>();
   }
+  S->last_hist_internal = false;
   if (!d_hist && S->always_hist_cap > 0) {  // always-on cost history (8 bytes per completed iteration and problem)
     hist_cap = S->always_hist_cap;
+    if (S->opt.max_iters > 0 && S->opt.max_iters < hist_cap) hist_cap = int(std::ceil(S->opt.max_iters));
     QCUDA(S, S->hist_d.ensure(sizeof(double) * size_t(hist_cap) * B));
     d_hist = S->hist_d.as<double>();
+    S->last_hist_internal = true;
   }
+  if (d_hist == S->hist_d.as<double>()) S->last_hist_internal = true;  // (the host path's own staging buffer)
+  S->last_hist_cap = d_hist ? hist_cap : 0;
+  S->last_hist_B = B;
   cudaStream_t st_ = S->stream;
   S->cur = st_;  // (an earlier solve that failed in its tail may have left the high-priority stream selected)
   S->in_tail = false;
@@ -448,7 +460,22 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
   k_cost_trajectory<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, d_traj, d_desired, B, N, Bd, st.cost);
   S->launches += 2;
 
-  const bool capture_debug = S->opt.populate_debug && d_debug && debug_cap > 0;
+  const bool ring_debug = S->opt.populate_debug && S->dbg_S > 0;
+  const bool capture_debug = (S->opt.populate_debug && d_debug && debug_cap > 0) || ring_debug;
+  DebugRing dr{};
+  if (ring_debug) {
+    const size_t slots = size_t(S->dbg_S) * S->dbg_ring;
+    QCUDA(S, S->dbg_traj.ensure(sizeof(double) * slots * N * 18));
+    QCUDA(S, S->dbg_iters.ensure(sizeof(int) * slots));
+    QCUDA(S, S->dbg_costs.ensure(sizeof(double) * slots));
+    QCUDA(S, S->dbg_count.ensure(sizeof(int) * size_t(S->dbg_S)));
+    QCUDA(S, cudaMemsetAsync(S->dbg_iters.ptr, 0xff, sizeof(int) * slots, st_));
+    QCUDA(S, cudaMemsetAsync(S->dbg_costs.ptr, 0, sizeof(double) * slots, st_));
+    QCUDA(S, cudaMemsetAsync(S->dbg_count.ptr, 0, sizeof(int) * size_t(S->dbg_S), st_));
+    dr = DebugRing{S->dbg_sample.as<int>(), S->dbg_S, S->dbg_ring, S->dbg_every, S->dbg_traj.as<double>(),
+                   S->dbg_iters.as<int>(), S->dbg_costs.as<double>(), S->dbg_count.as<int>(), S->dbg_time_aos};
+    S->dbg_N = N;
+  }
   const int P_alpha = S->opt.num_parallel_alphas > 1 ? S->opt.num_parallel_alphas : 1;
   if (P_alpha > 1) QCUDA(S, S->wide_d.ensure(sizeof(double) * size_t(P_alpha) * B));
   const bool can_persist = S->persistent_tail && P_alpha <= 1 && !S->generic_path && !S->force_t1 &&
@@ -552,9 +579,13 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         launch_rollout(S, ra, n_alive, st_);
       }
       ++S->launches;
-      if (capture_debug) {
+      if (d_debug && debug_cap > 0 && S->opt.populate_debug) {
         dim3 grid(blocks_for(n_alive, 128), 32);
         k_debug_capture<<<grid, 128, 0, st_>>>(pr, st, alive, n_alive, epoch, d_debug, debug_cap);
+        ++S->launches;
+      }
+      if (ring_debug) {
+        k_debug_ring_capture<<<S->dbg_S, 128, 0, st_>>>(pr, st, dr, epoch);
         ++S->launches;
       }
     }
@@ -766,7 +797,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
                           &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->totals_d, &S->tail_traj, &S->tail_gains,
                           &S->tail_des, &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map, &S->tail_lists,
-                          &S->rec_tail_d})
+                          &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
@@ -1013,6 +1044,7 @@ int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int B
     QCUDA(S, cudaMemsetAsync(d_debug, 0, need, st_));  // slots a problem never reaches
   }
   QCUDA(S, S->results_d.ensure(sizeof(qilqr_result_t) * size_t(B)));
+  S->dbg_time_aos = S->stage_a.as<double>();  // the uploaded input AoS: time_s of the sampled ILQRDebug trajectories
   HostCall &hc = S->host_call;
   hc = HostCall{};
   hc.B = B; hc.N = N;
@@ -1022,6 +1054,7 @@ int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int B
   hc.results = results;
   rc = solve_core(S, B, N, S->desired_soa.as<double>(), Bd, S->traj_soa.as<double>(), d_k, d_K, d_hist, hist_cap,
                   S->results_d.as<qilqr_result_t>(), d_debug, debug_cap, /*async_tail=*/true);
+  S->dbg_time_aos = nullptr;
   if (rc) return rc;
   hc.pending = true;
   return async ? QILQR_OK : solve_host_finish(S);
@@ -1046,6 +1079,59 @@ int qilqr_solve_host_finish(qilqr_solver_t *S) {
   if (!S) return QILQR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lock(S->mu);
   return solve_host_finish(S);
+}
+
+// ---- ILQRDebug at batch scale: sampling policy + ring buffer, always-on cost history ----------------------
+int qilqr_set_debug_sampling(qilqr_solver_t *S, int every_kth_iteration, const int32_t *problems, int num_problems,
+                             int ring_slots) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
+  if (num_problems <= 0 || !problems) {  // off
+    S->dbg_S = S->dbg_ring = S->dbg_every = 0;
+    return QILQR_OK;
+  }
+  if (every_kth_iteration < 1 || ring_slots < 1) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "every_kth_iteration and ring_slots must be >= 1");
+  QCUDA(S, cudaSetDevice(S->device));
+  QCUDA(S, S->dbg_sample.ensure(sizeof(int) * size_t(num_problems)));
+  QCUDA(S, cudaMemcpyAsync(S->dbg_sample.ptr, problems, sizeof(int) * size_t(num_problems), cudaMemcpyHostToDevice, S->stream));
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  S->dbg_S = num_problems;
+  S->dbg_ring = ring_slots;
+  S->dbg_every = every_kth_iteration;
+  S->dbg_N = 0;
+  return QILQR_OK;
+}
+int qilqr_read_debug_samples_host(qilqr_solver_t *S, double *traj, int32_t *iters, double *costs, int32_t *counts) {
+  if (!S) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
+  if (S->dbg_S <= 0 || S->dbg_N <= 0) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "no sampled ILQRDebug capture: call qilqr_set_debug_sampling, then solve with populate_debug");
+  QCUDA(S, cudaSetDevice(S->device));
+  const size_t slots = size_t(S->dbg_S) * S->dbg_ring;
+  // one asynchronous copy per array on the solver's stream (pinned destinations make them true DMA transfers)
+  if (traj) QCUDA(S, cudaMemcpyAsync(traj, S->dbg_traj.ptr, sizeof(double) * slots * S->dbg_N * 18, cudaMemcpyDeviceToHost, S->stream));
+  if (iters) QCUDA(S, cudaMemcpyAsync(iters, S->dbg_iters.ptr, sizeof(int) * slots, cudaMemcpyDeviceToHost, S->stream));
+  if (costs) QCUDA(S, cudaMemcpyAsync(costs, S->dbg_costs.ptr, sizeof(double) * slots, cudaMemcpyDeviceToHost, S->stream));
+  if (counts) QCUDA(S, cudaMemcpyAsync(counts, S->dbg_count.ptr, sizeof(int) * size_t(S->dbg_S), cudaMemcpyDeviceToHost, S->stream));
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  return QILQR_OK;
+}
+int qilqr_last_cost_history_host(qilqr_solver_t *S, int first, int count, double *out, int out_cap, int *stored_cap) {
+  if (!S || first < 0 || count < 0) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
+  if (stored_cap) *stored_cap = S->last_hist_cap;
+  if (!out || count == 0) return QILQR_OK;
+  if (S->last_hist_cap <= 0 || !S->last_hist_internal) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "the last solve kept no internal cost history (the caller passed its own buffer, or QILQR_ALWAYS_HIST_CAP=0)");
+  if (first + count > S->last_hist_B || out_cap < 1) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "cost history range out of the last batch");
+  QCUDA(S, cudaSetDevice(S->device));
+  const int cap = std::min(out_cap, S->last_hist_cap);
+  // [cap][B] on the device -> [count][out_cap] on the host
+  std::vector<double> rows(size_t(cap) * count);
+  QCUDA(S, cudaMemcpy2DAsync(rows.data(), sizeof(double) * count, S->hist_d.as<double>() + first,
+                             sizeof(double) * S->last_hist_B, sizeof(double) * count, cap, cudaMemcpyDeviceToHost, S->stream));
+  QCUDA(S, cudaStreamSynchronize(S->stream));
+  for (int b = 0; b < count; ++b)
+    for (int i = 0; i < out_cap; ++i) out[size_t(b) * out_cap + i] = i < cap ? rows[size_t(i) * count + b] : 0.0;
+  return QILQR_OK;
 }
 
 int qilqr_forward_sim_host(qilqr_solver_t *S, int B, int N, const double *current, const double *k, const double *K,

@@ -1133,6 +1133,45 @@ __global__ void k_debug_capture(Problem pr, SolveState st, const int *list, int 
     debug[(size_t(slot) * rows + r) * pr.B + b] = src[size_t(r) * pr.B + b];
 }
 
+// Sampled ILQRDebug stream (ilqr.hh:78-80 at batch scale): for the problems of `sample` (any order), keep the
+// trajectories of the iterations i with i % every == 0 in a ring of `ring` slots per problem -- the last `ring`
+// sampled iterations survive.  One block row per sampled problem; its ring is a contiguous array-of-structs block
+//   traj [S][ring][N][18]   (column 0 = time_s, taken from `time_aos` [B][N][18] when given, else the knot index)
+//   iters / costs [S][ring] the iteration index and new_cost of each slot (-1 / 0 where empty), count [S] the number
+//                           of sampled iterations so far (count > ring: the ring has wrapped).
+struct DebugRing {
+  const int *sample;   // [S] problem indices
+  int S, ring, every;
+  double *traj;
+  int *iters;
+  double *costs;
+  int *count;
+  const double *time_aos;
+};
+__global__ void k_debug_ring_capture(Problem pr, SolveState st, DebugRing dr, int epoch) {
+  const int s = blockIdx.x;
+  if (s >= dr.S) return;
+  const int b = dr.sample[s];
+  if (b < 0 || b >= pr.B || st.accepted_iter[b] != epoch) return;  // no trajectory accepted in this super-step
+  const int it = st.ndebug[b] - 1;  // index of the iteration that has just completed (ILQRDebug entry number)
+  if (it < 0 || it % dr.every != 0) return;
+  const int k = dr.count[s];  // (every thread of the block reads the same value; thread 0 bumps it at the end)
+  const int slot = k % dr.ring;
+  const double *src = st.sel[b] ? pr.buf1 : pr.buf0;
+  double *dst = dr.traj + (size_t(s) * dr.ring + slot) * pr.N * 18;
+  for (int e = threadIdx.x; e < pr.N * 18; e += blockDim.x) {
+    const int i = e / 18, c = e % 18;
+    dst[e] = (c == 0) ? (dr.time_aos ? dr.time_aos[(size_t(b) * pr.N + i) * 18] : double(i))
+                      : src[(size_t(i) * 17 + (c - 1)) * pr.B + b];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dr.iters[size_t(s) * dr.ring + slot] = it;
+    dr.costs[size_t(s) * dr.ring + slot] = st.cost[b];
+    dr.count[s] = k + 1;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // AoS [B][N][18] <-> SoA [N][17][B] transposition through shared memory.
 // Block: 32 problems x 18 components; grid.x = ceil(B/32), grid.y strides over knots.

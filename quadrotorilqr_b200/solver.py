@@ -76,6 +76,7 @@ class BatchILQR:
         ``MODEL_CORIOLIS`` select a second dynamics function behind the ModelT concept
         (``ilqr.hh:25-44``), ``MODEL_GENERIC`` the model-agnostic kernels for the reference model."""
         self._h = None
+        self._dbg = None
         self.options = options if options is not None else ILQROptions()
         self.dt_s = float(dt_s)
         m = _capi.Model()
@@ -174,6 +175,59 @@ class BatchILQR:
         return dict(traj=traj, results=res, k=k, K=K, cost_history=hist, debug=dbg)
 
     MAX_DEBUG_BYTES = 8 << 30  # refuse to stage more than this for a full ILQRDebug capture
+
+    # ---- ILQRDebug at batch scale (include/qilqr.h: qilqr_set_debug_sampling) ---------------------------
+    def set_debug_sampling(self, problems=None, every=1, ring=None):
+        """Capture ILQRDebug trajectories (``ilqr.hh:78-80``) for a sample only: ``problems`` = indices into the
+        batch, iterations ``i % every == 0``, the last ``ring`` sampled iterations per problem (default: enough for
+        every iteration up to ``max_iters``).  ``problems=None`` switches sampling off.  Needs
+        ``options.populate_debug``; read the rings back with :meth:`read_debug_samples` after a solve."""
+        if problems is None or len(problems) == 0:
+            self._check(_capi.lib().qilqr_set_debug_sampling(self._h, C.c_int(0), None, C.c_int(0), C.c_int(0)))
+            self._dbg = None
+            return
+        idx = np.ascontiguousarray(np.asarray(problems, dtype=np.int32))
+        if ring is None:
+            mi = self.options.convergence_criteria.max_iters
+            ring = max(1, int(np.ceil(min(mi, 4096.0) / every))) if np.isfinite(mi) and mi > 0 else 1
+        self._check(_capi.lib().qilqr_set_debug_sampling(self._h, C.c_int(int(every)), _ptr(idx),
+                                                         C.c_int(idx.size), C.c_int(int(ring))))
+        self._dbg = (idx, int(every), int(ring))
+
+    def read_debug_samples(self, n_knots, out=None):
+        """Rings of the last solve: dict with ``problems [S]``, ``traj [S, ring, N, 18]``, ``iters [S, ring]`` (-1 =
+        empty slot), ``costs [S, ring]``, ``counts [S]``; :meth:`debug_of` orders one problem's entries."""
+        idx, every, ring = self._dbg
+        S = idx.size
+        traj = out if out is not None else np.empty((S, ring, n_knots, 18))
+        iters = np.empty((S, ring), dtype=np.int32)
+        costs = np.empty((S, ring))
+        counts = np.empty(S, dtype=np.int32)
+        self._check(_capi.lib().qilqr_read_debug_samples_host(self._h, _ptr(traj), _ptr(iters), _ptr(costs),
+                                                              _ptr(counts)))
+        return dict(problems=idx, traj=traj, iters=iters, costs=costs, counts=counts, every=every, ring=ring)
+
+    @staticmethod
+    def debug_of(samples, s):
+        """(iteration indices, trajectories, costs) of sampled problem number ``s``, oldest first."""
+        it = samples["iters"][s]
+        order = np.argsort(it[it >= 0], kind="stable")
+        sel = np.where(it >= 0)[0][order]
+        return it[sel], samples["traj"][s, sel], samples["costs"][s, sel]
+
+    def last_cost_history(self, first=0, count=None, cap=None):
+        """Per-iteration costs of the last solve, kept on the device for every problem (always on):
+        ``[count, cap]``, zero-padded; a problem's valid entries are ``results['num_debug']``."""
+        stored = C.c_int(0)
+        self._check(_capi.lib().qilqr_last_cost_history_host(self._h, C.c_int(0), C.c_int(0), None, C.c_int(0),
+                                                             C.byref(stored)))
+        cap = int(cap or stored.value)
+        if count is None:
+            raise ValueError("count (number of problems) is required")
+        out = np.zeros((count, max(cap, 1)))
+        self._check(_capi.lib().qilqr_last_cost_history_host(self._h, C.c_int(first), C.c_int(count), _ptr(out),
+                                                             C.c_int(out.shape[1]), C.byref(stored)))
+        return out
 
     def solve_host_begin(self, initial, desired, out_traj, results):
         """First half of :meth:`solve_host_buffers` (``qilqr_solve_host_begin``): returns once the device finishes the
