@@ -178,12 +178,154 @@ def reference_arm(args, rank, world):
     return 0
 
 
+def other_config(args, local_rank):
+    """`--config c4|c5`: the long-horizon and the receding-horizon BASELINE configs on one GPU, one JSON line each with
+    the roofline of the backward pass measured the same way as for the headline (CUDA events around every launch of a
+    profiled repetition).  Not the driver's headline: that is `--config c3` (the default)."""
+    import ctypes
+    import dataclasses
+
+    import torch
+
+    from quadrotorilqr_b200 import BatchILQR, RESULT_DTYPE, _capi, problems
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+
+    def mk(model, opts):
+        return BatchILQR(model["mass_kg"], model["inertia"], model["arm_length_m"], model["torque_to_thrust_ratio_m"],
+                         model["g_mpss"], model["Q"], model["R"], model["dt_s"], opts, device=local_rank)
+
+    def device_problem(s_, x0, desired, N):
+        B = x0.shape[0]
+        x0_soa = torch.from_numpy(np.ascontiguousarray(x0.T)).to(dev)
+        init = torch.empty((N, 17, B), dtype=torch.float64, device=dev)
+        des = torch.empty((N, 17, 1), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        s_.pack_trajectory_device(torch.from_numpy(desired[None].copy()).to(dev), des)
+        s_.rollout_constant_control_device(x0_soa, desired[0, 14:18], init)
+        torch.cuda.synchronize()
+        return x0_soa, init, des
+
+    peak = ctypes.c_double(0.0)
+    _capi.lib().qilqr_measure_fp64_peak(ctypes.c_int(local_rank), ctypes.byref(peak))
+    sampler = ClockSampler(local_rank)
+    if args.config == "c4":
+        N, dt_s, B = 1000, 0.02, args.batch if args.batch != 65536 else 4096
+        m = dict(problems.hover_model(), dt_s=dt_s)
+        o = dataclasses.replace(problems.default_options(False), symmetrize_vxx=True, num_parallel_alphas=8)
+        P = max(1, min(args.pipeline, 4))  # batches in flight (6 GB of workspace each)
+        handles = [mk(m, o) for _ in range(P)]
+        s_ = handles[0]
+        d = problems.figure_eight_desired(N, dt_s)
+        _, init, des = device_problem(s_, problems.figure_eight_initial_states(B, d), d, N)
+        works = [torch.empty_like(init) for _ in range(P)]
+        ress = [torch.zeros(B * 24, dtype=torch.uint8, device=dev) for _ in range(P)]
+        streams = [torch.cuda.ExternalStream(h_.stream_handle, device=dev) for h_ in handles]
+        res = ress[0]
+
+        def step(j=0):
+            with torch.cuda.stream(streams[j]):
+                works[j].copy_(init, non_blocking=True)
+            handles[j].solve_device(works[j], des, results=ress[j])
+
+        def run(n_each):
+            ths = [threading.Thread(target=lambda j=j: [step(j) for _ in range(n_each)]) for j in range(P)]
+            for t_ in ths:
+                t_.start()
+            for t_ in ths:
+                t_.join()
+            torch.cuda.synchronize()
+
+        run(max(1, args.warmup // 2))
+        t0 = time.perf_counter()
+        for _ in range(2):
+            step(0)
+        torch.cuda.synchronize()
+        serial_dt = (time.perf_counter() - t0) / 2
+        sampler.start()
+        n_each = max(2, args.steps // 5)
+        steps = n_each * P
+        t0 = time.perf_counter()
+        run(n_each)
+        dt = (time.perf_counter() - t0) / steps
+        clocks = sampler.stop()
+        s_.set_profiling(True)
+        step(0)
+        torch.cuda.synchronize()
+        st = s_.last_solve_stats()
+        s_.set_profiling(False)
+        r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+        conv = int(np.sum((r["status"] == 1) | (r["status"] == 2)))
+        its = int(r["backward_passes"].sum())
+        achieved = st["backward_problem_knots"] * F_BWD / (st["backward_ms"] * 1e-3) / 1e12
+        line = {"metric": "converged iLQR solves/sec (BASELINE config 4: N=1000 figure-eight tracking, batch 4096, 8 parallel "
+                          "line-search step sizes, symmetrised V_xx, FP64)", "value": conv / dt, "unit": UNIT,
+                "n_gpus": 1, "steps": steps, "warmup": max(1, args.warmup // 2), "ms_per_step": 1e3 * dt,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"c4: batch {B}, N={N}, dt={dt_s}, figure-eight p(t)=(2 sin wt, 2 sin wt cos wt, 1), "
+                                       "x0 = p(0) + U[-0.3,0.3]^3, hover-thrust initial rollout",
+                           "pipeline": f"{P} batches in flight (one solver handle + host thread + stream pair each)"},
+                "serial_ms_per_step": 1e3 * serial_dt, "serial_value": conv / serial_dt,
+                "iterations_per_solve": its / B, "max_iterations": int(r["backward_passes"].max()),
+                "problem_knot_iterations_per_s": its * N / dt, "us_per_iteration": 1e6 * dt / its,
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
+                "roofline": {"kernel": "backward pass = k_linearise + k_riccati_g4", "bound": "fp64", "achieved": achieved,
+                             "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
+                             "frac_definition": "dense as-written reference FLOPs / CUDA-event time of every backward launch "
+                                                "of one profiled solve / measured DFMA peak (512 Riccati warps on 148 SMs: "
+                                                "latency-bound)",
+                             "share_of_profiled_step": st["backward_ms"] / (st["backward_ms"] + st["rollout_ms"]),
+                             "rollout_ms": st["rollout_ms"], "backward_ms": st["backward_ms"], "traffic": None}}
+    else:  # c5
+        N, B, T = N_KNOTS, (args.batch if args.batch != 65536 else 16384), max(10, args.steps * 5)
+        m, o = problems.hover_model(), problems.default_options(False)
+        s_ = mk(m, o)
+        d = problems.hover_desired_trajectory(N)
+        plant, traj, des = device_problem(s_, problems.hover_initial_states(B, seed=5), d, N)
+        rng = np.random.Generator(np.random.Philox(key=55))
+        dist = torch.from_numpy(np.ascontiguousarray(rng.uniform(-0.01, 0.01, (6, B)))).to(dev)
+        s_.mpc_run_device(max(2, args.warmup), traj, des, plant, disturbance=dist)
+        torch.cuda.synchronize()
+        sampler.start()
+        t0 = time.perf_counter()
+        tot = s_.mpc_run_device(T, traj, des, plant, disturbance=dist)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        s_.set_profiling(True)
+        s_.mpc_run_device(5, traj, des, plant, disturbance=dist)
+        torch.cuda.synchronize()
+        st = s_.last_solve_stats()
+        s_.set_profiling(False)
+        achieved = st["backward_problem_knots"] * F_BWD / (st["backward_ms"] * 1e-3) / 1e12 if st["backward_ms"] else None
+        line = {"metric": "warm-started iLQR re-solves/sec (BASELINE config 5: receding-horizon MPC, 16384 quadrotors "
+                          "closed loop, N=40, FP64)", "value": tot["resolves"] / dt, "unit": "re-solves/s",
+                "n_gpus": 1, "steps": T, "warmup": max(2, args.warmup), "ms_per_step": 1e3 * dt / T,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"c5: {B} quadrotors x {T} closed-loop steps, N={N}, plant = discrete_dynamics + constant "
+                                       "body-velocity disturbance U[-0.01,0.01]^6, warm start = previous solution shifted one knot"},
+                "iterations_per_resolve": tot["backward_passes"] / tot["resolves"], "not_converged": tot["not_converged"],
+                "gpu_launches": int(st["kernel_launches"]), "clocks": clocks,
+                "roofline": {"kernel": "backward pass = k_linearise + k_riccati_g4 / k_riccati_g16", "bound": "fp64",
+                             "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                             "frac": achieved / peak.value if (achieved and peak.value) else None,
+                             "frac_definition": "dense as-written reference FLOPs / CUDA-event time of every backward launch of 5 "
+                                                "profiled closed-loop steps / measured DFMA peak",
+                             "share_of_profiled_step": st["backward_ms"] / max(1e-9, st["backward_ms"] + st["rollout_ms"]),
+                             "traffic": None}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 (default) = the headline, BASELINE config 3; c4 / c5: long-horizon and MPC configs, one GPU")
     ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--cpu-sample-per-core", type=int, default=1024)
@@ -215,6 +357,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
+    if args.config != "c3":
+        return other_config(args, local_rank)
     import ctypes
 
     dist = None

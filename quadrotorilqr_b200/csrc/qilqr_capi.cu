@@ -24,6 +24,7 @@
 #include "qilqr_backward_split.cuh"
 #include "qilqr_backward_dense.cuh"
 #include "qilqr_tail_persistent.cuh"
+#include "qilqr_riccati_g16.cuh"
 
 using namespace qilqr;
 
@@ -103,6 +104,10 @@ struct qilqr_solver {
   bool split_backward = true;    // linearise kernel + TMA-fed Riccati kernel (default) vs the fused quad kernel
   bool rollout_ws = true;        // role-specialised rollout kernel (3 warps per 32 problems); QILQR_ROLLOUT=thread: one thread per problem
   int ws_threshold = 4096;       // ... used for launches of at most this many problems (latency-bound); QILQR_WS_THRESHOLD
+  bool wide_first = false;       // QILQR_WIDE_FIRST=1: parallel step sizes from the first candidate of every line search
+  int g16_threshold = 1184;      // Riccati sweep with 16 lanes per problem for launches of at most this many problems: one
+                                 // tile of 8 per SM (beyond that k_riccati_g4's lower instruction count wins)
+                                 // (k_riccati_g16; QILQR_G16_THRESHOLD, 0 = never)
   bool generic_path = false;     // model-agnostic kernels (dense J_x, J_u): any model variant, or forced for cross-checks
   std::vector<TimedSpan> spans;
   std::vector<cudaEvent_t> event_pool;
@@ -332,6 +337,7 @@ cudaError_t configure_kernels() {
   if ((e = opt_in_smem(k_riccati_g4<false>, sizeof(double) * g4::split_smem_doubles(false) + riccati_extra_smem())) != cudaSuccess) return e;
   if ((e = opt_in_smem(k_riccati_g4<true>, sizeof(double) * g4::split_smem_doubles(true) + riccati_extra_smem())) != cudaSuccess) return e;
   if ((e = opt_in_smem(k_riccati_dense, sizeof(double) * dn::smem_doubles())) != cudaSuccess) return e;
+  if ((e = opt_in_smem(k_riccati_g16, sizeof(double) * g16::smem_doubles())) != cudaSuccess) return e;
   if ((e = opt_in_smem(k_tail_persistent<false>, sizeof(double) * tp::smem_doubles(false))) != cudaSuccess) return e;
   if ((e = opt_in_smem(k_tail_persistent<true>, sizeof(double) * tp::smem_doubles(true))) != cudaSuccess) return e;
   return cudaSuccess;
@@ -351,7 +357,10 @@ int launch_split(qilqr_solver *S, const BackwardArgs &ba) {
   const size_t smem = sizeof(double) * g4::split_smem_doubles(DENSEQ) + riccati_extra_smem();
   const size_t threads = size_t(n8) * ba.pr.N;
   k_linearise<DENSEQ><<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
-  k_riccati_g4<DENSEQ><<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  if (!DENSEQ && ba.n <= S->g16_threshold)  // latency-bound launch: 16 lanes per problem (bit-identical results)
+    k_riccati_g16<<<n8 / 8, 128, sizeof(double) * g16::smem_doubles(), S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  else
+    k_riccati_g4<DENSEQ><<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   ++S->launches;
   return QILQR_OK;
 }
@@ -370,8 +379,8 @@ int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
 // forward_sim (+ cost, + line-search bookkeeping) with the dynamics of the configured model
 void launch_rollout(qilqr_solver *S, const RolloutArgs &ra, int threads, cudaStream_t st) {
   if (S->generic_path) k_rollout<true><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
-  // (with parallel step sizes every evaluation, wide or not, stays on the one-thread-per-problem kernel)
-  else if (S->rollout_ws && S->opt.num_parallel_alphas <= 1 && threads <= S->ws_threshold) k_rollout_ws<<<blocks_for(threads, 32), 96, 0, st>>>(S->p, ra);
+  // (the parallel step-size rounds stay on the one-thread-per-problem kernel; the two kernels are bit-identical)
+  else if (S->rollout_ws && ra.mode != MODE_WIDE && threads <= S->ws_threshold) k_rollout_ws<<<blocks_for(threads, 32), 96, 0, st>>>(S->p, ra);
   else k_rollout<false><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
 }
 int launch_backward(qilqr_solver *S, const BackwardArgs &ba) {
@@ -551,7 +560,7 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       break;
     }
     if (n_active > 0) {
-      BackwardArgs ba{pr, st, active, n_active, epoch, P_alpha > 1 ? 1 : 0, 1, nullptr, nullptr};
+      BackwardArgs ba{pr, st, active, n_active, epoch, P_alpha > 1 ? (S->wide_first ? 2 : 1) : 0, 1, nullptr, nullptr};
       {
         SpanGuard g(S, 0);
         if ((rc = launch_backward(S, ba))) return rc;
@@ -560,20 +569,20 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       if (!S->in_tail) S->stats.backward_problem_knots_bulk += int64_t(n_active) * N;
       ++S->launches;
     }
-    if (P_alpha > 1 && epoch > 0) {
+    if (P_alpha > 1 && epoch > 0 && (S->wide_first || n_alive > n_active)) {  // someone is backtracking
       // parallel line search: P_alpha step sizes per problem as independent cost-only rollouts, then the first
       // (largest) one that passes the Armijo test -- what the sequential search would accept
-      RolloutArgs rw{pr, st, alive, n_alive, epoch, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha, 1};
+      RolloutArgs rw{pr, st, alive, n_alive, epoch, MODE_WIDE, nullptr, nullptr, nullptr, S->wide_d.as<double>(), P_alpha, 1, 0};
       {
         SpanGuard g(S, 1);
         launch_rollout(S, rw, n_alive * P_alpha, st_);
       }
-      k_select_alpha<<<blocks_for(n_alive, 128), 128, 0, st_>>>(S->p, st, alive, n_alive, B_eff, S->wide_d.as<double>(), P_alpha);
+      k_select_alpha<<<blocks_for(n_alive, 128), 128, 0, st_>>>(S->p, st, alive, n_alive, B_eff, S->wide_d.as<double>(), P_alpha, epoch);
       S->launches += 2;
     }
     {
       // forward_sim + cost + Armijo / convergence bookkeeping for every problem that is searching at its alpha[b]
-      RolloutArgs ra{pr, st, alive, n_alive, epoch, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1, 1};
+      RolloutArgs ra{pr, st, alive, n_alive, epoch, MODE_SOLVE, nullptr, nullptr, nullptr, nullptr, 1, 1, P_alpha > 1 ? 1 : 0};
       {
         SpanGuard g(S, 1);
         launch_rollout(S, ra, n_alive, st_);
@@ -760,6 +769,8 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   if (const char *e = std::getenv("QILQR_PERSIST_THRESHOLD")) S->persist_threshold = std::atoi(e);
   if (const char *e = std::getenv("QILQR_ALWAYS_HIST_CAP")) S->always_hist_cap = std::max(0, std::atoi(e));
   if (const char *e = std::getenv("QILQR_WS_THRESHOLD")) S->ws_threshold = std::atoi(e);
+  if (const char *e = std::getenv("QILQR_G16_THRESHOLD")) S->g16_threshold = std::atoi(e);
+  if (const char *e = std::getenv("QILQR_WIDE_FIRST")) S->wide_first = std::atoi(e) != 0;
   if (const char *e = std::getenv("QILQR_KPP")) {
     const int v = std::atoi(e);
     if (v == 1 || v == 2 || v == 4) S->g4_kpp = v;
@@ -1228,6 +1239,12 @@ int qilqr_line_search_host(qilqr_solver_t *S, int B, int N, const double *desire
       !status || B <= 0 || N <= 0 || (Bd != 1 && Bd != B))
     return QILQR_ERR_INVALID_ARGUMENT;
   QENTER(S);
+  if (S->p.ls_max_iters <= 0) {
+    // line_search's loop (ilqr.hh:178-193) evaluates no candidate at all and throws
+    std::memcpy(out_traj, current, sizeof(double) * size_t(B) * N * 18);
+    for (int b = 0; b < B; ++b) { status[b] = QILQR_ERR_LINE_SEARCH; step[b] = 1.0; new_cost[b] = current_cost[b]; }
+    return QILQR_OK;
+  }
   QCUDA(S, cudaSetDevice(S->device));
   cudaStream_t st_ = S->stream;
   int rc = ensure_state(S, B);

@@ -135,7 +135,31 @@ struct RolloutArgs {
   int palpha;        // MODE_WIDE: step sizes evaluated per problem
   int check_phase;   // MODE_SOLVE / MODE_WIDE: `list` is the list of ALIVE problems; skip those that are not in
                      // PHASE_SEARCH / PHASE_WIDE
+  int wide_on_reject;  // MODE_SOLVE with parallel step sizes: a rejected candidate sends the problem to PHASE_WIDE
+                       // (the next `num_parallel_alphas` step sizes are then evaluated concurrently)
 };
+
+// The candidate trajectory of problem b (in its other buffer, cost `cost`) is accepted: it becomes the current
+// trajectory; ILQRDebug / cost history entry; exit B of solve() (ilqr.hh:72-84).
+QD void accept_candidate(const DeviceParams &p, const SolveState &st, int B, int b, int epoch, int mode, int it,
+                         double cur_cost, double cost) {
+  st.sel[b] ^= 1;
+  st.cost[b] = cost;
+  st.accepted_iter[b] = epoch;
+  const int nd = st.ndebug[b];
+  if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
+  st.ndebug[b] = nd + 1;
+  if (mode == MODE_SOLVE && it > 0 && is_converged(p, cur_cost, cost)) {
+    st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
+    st.phase[b] = PHASE_DONE;
+  } else if (mode == MODE_LINE_SEARCH) {
+    st.phase[b] = PHASE_DONE;
+  } else {
+    // the loop bound of ilqr.hh:58, `i < max_iters` with max_iters a double, for the next i = it + 1
+    // (k_finalize turns "done without a status" into QILQR_STATUS_MAX_ITERS)
+    st.phase[b] = (double(it + 1) < p.max_iters) ? PHASE_ACTIVE : PHASE_DONE;
+  }
+}
 
 // line_search() / solve() bookkeeping after one candidate rollout of problem b (ilqr.hh:70-84, 182-193)
 QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, double alpha, double cost) {
@@ -155,22 +179,7 @@ QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, doubl
     accept = (cost - cur_cost < desired);  // ilqr.hh:186; NaN -> reject
   }
   if (accept) {
-    st.sel[b] ^= 1;
-    st.cost[b] = cost;
-    st.accepted_iter[b] = a.iter;
-    const int nd = st.ndebug[b];
-    if (st.cost_hist && nd < st.hist_cap) st.cost_hist[size_t(nd) * B + b] = cost;
-    st.ndebug[b] = nd + 1;
-    if (a.mode == MODE_SOLVE && it > 0 && is_converged(p, cur_cost, cost)) {
-      st.status[b] = QILQR_STATUS_CONVERGED_ACTUAL;  // ilqr.hh:82-84
-      st.phase[b] = PHASE_DONE;
-    } else if (a.mode == MODE_LINE_SEARCH) {
-      st.phase[b] = PHASE_DONE;
-    } else {
-      // the loop bound of ilqr.hh:58, `i < max_iters` with max_iters a double, for the next i = it + 1
-      // (k_finalize turns "done without a status" into QILQR_STATUS_MAX_ITERS)
-      st.phase[b] = (double(it + 1) < p.max_iters) ? PHASE_ACTIVE : PHASE_DONE;
-    }
+    accept_candidate(p, st, B, b, a.iter, a.mode, it, cur_cost, cost);
   } else {
     st.alpha[b] = alpha * p.step_update;  // ilqr.hh:189
     const int ls = st.ls_iter[b] + 1;
@@ -178,6 +187,8 @@ QD void rollout_finish(const DeviceParams &p, const RolloutArgs &a, int b, doubl
     if (ls >= p.ls_max_iters) {
       st.status[b] = isfinite(cost) ? QILQR_STATUS_LINE_SEARCH_FAILED : QILQR_STATUS_NONFINITE;  // ilqr.hh:191-193
       st.phase[b] = PHASE_DONE;
+    } else if (a.wide_on_reject) {
+      st.phase[b] = PHASE_WIDE;
     }
   }
 }
@@ -202,8 +213,11 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
   if (a.mode == MODE_FORWARD) {
     cur = a.cur; cand = a.out; alpha = a.alpha_in[b];
   } else if (a.mode == MODE_WIDE) {
-    cur = a.st.sel[b] ? a.pr.buf1 : a.pr.buf0;
-    cand = nullptr;
+    const int s = a.st.sel[b];
+    cur = s ? a.pr.buf1 : a.pr.buf0;
+    // the first step size of a round also writes its trajectory: it is the one the search accepts nearly always,
+    // and k_select_alpha can then accept it without another rollout
+    cand = (wide_j == 0) ? (s ? a.pr.buf0 : a.pr.buf1) : nullptr;
     alpha = a.st.alpha[b];
     for (int j = 0; j < wide_j; ++j) alpha *= p.step_update;  // the same products as the sequential search
   } else {
@@ -239,7 +253,7 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
       for (int s = 1; s < 12; ++s) Kd = QFMA(gK[12 * j + s], d[s], Kd);
       u[j] = QFMA(alpha, gk[j], ubar[j]) + Kd;
     }
-    if (a.mode != MODE_WIDE) store_point(cand, i, B, b, x, u);
+    if (cand) store_point(cand, i, B, b, x, u);
     if (want_cost) {
       double xd[13], ud[4], dx[12], du[4];
       load_point(a.pr.desired, i, Bd, bd, xd, ud);
@@ -528,7 +542,7 @@ struct BackwardArgs {
   const int *list;
   int n;
   int iter;             // the solver's super-step number (informational)
-  int wide;             // 1: step sizes are evaluated in parallel (PHASE_WIDE after the first iteration)
+  int wide;             // 1: parallel step sizes after the first rejection; 2: from the first candidate on
   int solve_mode;       // 1: solve() bookkeeping (exit A); 0: plain backwards_pass
   const double *traj;   // solve_mode == 0 only
   double *terms_out;    // solve_mode == 0 only: [B][2]
@@ -559,7 +573,10 @@ QD void backward_finish(const DeviceParams &p, const BackwardArgs &a, int b, dou
   } else {
     st.alpha[b] = 1.0;
     st.ls_iter[b] = 0;
-    st.phase[b] = (a.wide && it > 0) ? PHASE_WIDE : PHASE_SEARCH;  // iteration 0 is an unconditional full step
+    // the full step first, on its own: it is the one the search accepts nearly always (and iteration 0 takes it
+    // unconditionally); with parallel step sizes (a.wide) a rejection sends the problem to PHASE_WIDE, unless
+    // a.wide == 2 (QILQR_WIDE_FIRST=1: every search starts with a parallel round)
+    st.phase[b] = (a.wide == 2 && it > 0) ? PHASE_WIDE : PHASE_SEARCH;
   }
 }
 
@@ -852,7 +869,7 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
 // `rollouts` and `ls_iter` count what the sequential search would have evaluated.
 // ---------------------------------------------------------------------------
 __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveState st, const int *list, int n, int B,
-                               const double *wide_cost, int palpha) {
+                               const double *wide_cost, int palpha, int epoch) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int b = list ? list[t] : t;
@@ -871,7 +888,15 @@ __global__ void k_select_alpha(const __grid_constant__ DeviceParams p, SolveStat
       st.alpha[b] = alpha;
       st.ls_iter[b] = ls;
       st.rollouts[b] += ls - ls0;
-      st.phase[b] = PHASE_SEARCH;
+      if (j == 0) {
+        // the round's first step size: its trajectory is already in the candidate buffer -- accept it here, as
+        // rollout_finish would after one more (identical) rollout
+        st.rollouts[b] += 1;
+        st.new_cost[b] = cost;
+        accept_candidate(p, st, B, b, epoch, MODE_SOLVE, st.bwd[b] - 1, cur_cost, cost);
+      } else {
+        st.phase[b] = PHASE_SEARCH;  // rolled out (and accepted) at this alpha by the next launch
+      }
       return;
     }
     alpha *= p.step_update;
