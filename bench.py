@@ -553,10 +553,48 @@ def main():
         e2e = {"t": e2e_t, "steps": e2e_steps, "converged": conv2,
                "h2d": B * N * 18 * 8 + N * 18 * 8, "d2h": B * N * 18 * 8 + B * 24}
 
+        # the same batches through qilqr_solve_from_controls_host: x0 and ONE nominal control sequence go up (the
+        # initial trajectory of this workload is their open-loop rollout), full trajectories come back
+        x0_host = torch.from_numpy(np.ascontiguousarray(x0)).pin_memory()
+        u_nom = np.ascontiguousarray(np.tile(desired[0, 14:18], (N, 1)))
+
+        def ctl_begin(j, h):
+            solvers[j][h].solve_from_controls(x0_host, u_nom, desired_c, out_traj=out_host[j][h], results=res_host[j][h],
+                                              begin_only=True)
+
+        run_pipelined(ctl_begin, host_finish, P * H)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipelined(ctl_begin, host_finish, e2e_steps, stagger_s)
+        barrier()
+        e2e["ctl_t"] = time.perf_counter() - t0
+        r3 = np.frombuffer(res_host[0][0].numpy().tobytes(), dtype=RESULT_DTYPE)
+        e2e["ctl_converged"] = int(np.sum((r3["status"] == 1) | (r3["status"] == 2)))
+        e2e["ctl_same_results"] = bool(np.array_equal(r3, r2))
+        e2e["ctl_h2d"] = B * 13 * 8 + N * 4 * 8 + N * 18 * 8
+
+        # what the host's memory system gives this rank while every rank copies at once: the H2D + D2H traffic of one
+        # step (pinned buffers, both directions concurrently) -- the denominator for the end-to-end scaling
+        dma_dev = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
+        dma_dev2 = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            with torch.cuda.stream(s_up):
+                dma_dev.copy_(init_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                out_host[0][0].copy_(dma_dev2, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e["dma_gbs_per_direction"] = 4 * B * N * 18 * 8 / (time.perf_counter() - t0) / 1e9
+        del dma_dev, dma_dev2
+
     # ---- reduce over ranks (NCCL: stats and max time only) ---------------------------------------
     vec = torch.tensor([dev_ms, t_wall * 1e3, float(converged), float(prob_iters), float(ls_failed),
                         float(max_iter_hit), float(launches), e2e["t"] if e2e else 0.0,
-                        float(e2e["converged"]) if e2e else 0.0], dtype=torch.float64, device=dev)
+                        float(e2e["converged"]) if e2e else 0.0, e2e["ctl_t"] if e2e else 0.0,
+                        float(e2e["ctl_converged"]) if e2e else 0.0,
+                        e2e["dma_gbs_per_direction"] if e2e else 0.0], dtype=torch.float64, device=dev)
     gathered_converged = None
     if dist is not None:
         mx = vec.clone()
@@ -689,6 +727,18 @@ def main():
                        "steps": e2e["steps"],
                        "api": "qilqr_solve_host_begin / _finish (pinned host AoS in/out, results struct per problem; "
                               "same results as qilqr_solve_host)"}
+        line["e2e_from_controls"] = {
+            "value": sm[10] / (mx[9] / e2e["steps"]), "unit": UNIT, "ms_per_step": 1e3 * mx[9] / e2e["steps"],
+            "h2d_bytes_per_step": e2e["ctl_h2d"], "d2h_bytes_per_step": e2e["d2h"], "same_results_as_e2e": e2e["ctl_same_results"],
+            "api": "qilqr_solve_from_controls_host_begin / qilqr_solve_host_finish: x0 [B][13] and one nominal control "
+                   "sequence in (this workload's initial trajectories are their open-loop rollout, made on the device), "
+                   "full trajectories [B][N][18] out"}
+        line["host_dma"] = {
+            "gbs_per_direction_all_gpus": sm[11], "gbs_per_direction_per_gpu": sm[11] / world,
+            "note": "pinned-memory H2D and D2H copies of one step's trajectories, both directions at once, on every rank at "
+                    "the same time (no compute): what the host's memory system and PCIe fabric give the end-to-end path. "
+                    f"A step moves {(e2e['h2d'] + e2e['d2h']) / 1e6:.0f} MB per GPU through it (e2e) or "
+                    f"{(e2e['ctl_h2d'] + e2e['d2h']) / 1e6:.0f} MB (e2e_from_controls)"}
     if not args.no_cpu_baseline and world >= 1:
         import oracle as O
 

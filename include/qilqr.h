@@ -159,6 +159,22 @@ int qilqr_solve_host_begin(qilqr_solver_t *solver, int batch, int n_knots, const
                            const double *initial, double *out_traj, qilqr_result_t *results);
 int qilqr_solve_host_finish(qilqr_solver_t *solver);
 
+/* The usual calling convention of an iLQR solver: the initial guess is a control sequence.  x0 [batch][13],
+ * controls [control_count][n_knots][4] with control_count = 1 (one nominal sequence for the whole batch) or batch;
+ * the initial trajectory ILQR::solve starts from (ilqr.hh:53-56) is their open-loop rollout under
+ * QuadrotorModel::discrete_dynamics, made on the device, with time_s = knot * dt_s.  Identical, bit for bit, to
+ * rolling the trajectory out first (qilqr_forward_sim_host with zero gains) and calling qilqr_solve_host -- but
+ * 13 + 4 n_knots doubles go up per problem instead of 18 n_knots.  out_traj [batch][n_knots][18] and / or
+ * out_controls [batch][n_knots][4] (either may be NULL, not both): a receding-horizon caller needs only the
+ * controls.  _begin / qilqr_solve_host_finish: as for qilqr_solve_host_begin. */
+int qilqr_solve_from_controls_host(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                                   int desired_count, const double *x0, const double *controls, int control_count,
+                                   double *out_traj, double *out_controls, qilqr_result_t *results);
+int qilqr_solve_from_controls_host_begin(qilqr_solver_t *solver, int batch, int n_knots, const double *desired,
+                                         int desired_count, const double *x0, const double *controls,
+                                         int control_count, double *out_traj, double *out_controls,
+                                         qilqr_result_t *results);
+
 /* ---------------------------------------------------------------------------
  * ILQRDebug at batch scale (ilqr.hh:78-80, ilqr_debug.hh:9-22, ilqr_debug.proto:7-14).  A full capture is
  * iterations x n_knots x 144 bytes per problem (35 GB for 65536 problems): qilqr_solve_host's debug_traj argument

@@ -96,7 +96,8 @@ EXPORTED_SYMBOLS = [
     "qilqr_mpc_advance_device", "qilqr_mpc_run_device", "qilqr_check_model",
     "qilqr_set_model_variant", "qilqr_build_info", "qilqr_solve_host_begin", "qilqr_solve_host_finish",
     "qilqr_solve_device_begin", "qilqr_solve_device_finish", "qilqr_set_debug_sampling",
-    "qilqr_read_debug_samples_host", "qilqr_last_cost_history_host",
+    "qilqr_read_debug_samples_host", "qilqr_last_cost_history_host", "qilqr_solve_from_controls_host",
+    "qilqr_solve_from_controls_host_begin",
 ]
 
 MODEL_REFERENCE = 0

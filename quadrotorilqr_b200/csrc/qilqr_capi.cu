@@ -74,6 +74,7 @@ struct HostCall {  // where the results of a host-buffer solve go (qilqr_solve_h
   bool pending = false;
   int B = 0, N = 0, hist_cap = 0, debug_cap = 0;
   double *out_traj = nullptr, *out_k = nullptr, *out_K = nullptr, *cost_hist = nullptr, *debug_traj = nullptr;
+  double *out_controls = nullptr;  // qilqr_solve_from_controls_host: [B][N][4]
   qilqr_result_t *results = nullptr;
 };
 }  // namespace
@@ -114,7 +115,7 @@ struct qilqr_solver {
 
   // workspace
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
-      hist_d, debug_d, misc, wide_d, rec_d, totals_d;
+      hist_d, debug_d, misc, wide_d, rec_d, totals_d, stage_d;
   // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
   DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map, tail_lists, rec_tail_d;
   bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
@@ -808,7 +809,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
                           &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->totals_d, &S->tail_traj, &S->tail_gains,
                           &S->tail_des, &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map, &S->tail_lists,
-                          &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count})
+                          &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count, &S->stage_d})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->h_counts) cudaFreeHost(S->h_counts);
@@ -973,9 +974,18 @@ int solve_host_finish(qilqr_solver *S) {
   cudaStream_t st_ = S->stream;
   const int B = hc.B, N = hc.N;
   const size_t traj_bytes = sizeof(double) * size_t(B) * N * 18;
-  // results back: stage_a still holds the input AoS (time_s column), unpack over it
-  unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
-  QCUDA(S, cudaMemcpyAsync(hc.out_traj, S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+  if (hc.out_traj) {
+    // results back: stage_a still holds the input AoS (time_s column), unpack over it
+    unpack_traj(S, B, N, S->traj_soa.as<double>(), S->stage_a.as<double>());
+    QCUDA(S, cudaMemcpyAsync(hc.out_traj, S->stage_a.ptr, traj_bytes, cudaMemcpyDeviceToHost, st_));
+  }
+  if (hc.out_controls) {
+    const size_t n4 = size_t(B) * N * 4;
+    QCUDA(S, S->stage_d.ensure(sizeof(double) * n4));
+    k_extract_controls<<<unsigned((n4 + 255) / 256), 256, 0, st_>>>(S->traj_soa.as<double>(), S->stage_d.as<double>(), B, N);
+    ++S->launches;
+    QCUDA(S, cudaMemcpyAsync(hc.out_controls, S->stage_d.ptr, sizeof(double) * n4, cudaMemcpyDeviceToHost, st_));
+  }
   if (hc.results) QCUDA(S, cudaMemcpyAsync(hc.results, S->results_d.ptr, sizeof(qilqr_result_t) * size_t(B), cudaMemcpyDeviceToHost, st_));
   if (hc.out_k) {
     QCUDA(S, S->stage_c.ensure(sizeof(double) * size_t(N) * 48 * B));
@@ -1020,10 +1030,17 @@ int solve_host_finish(qilqr_solver *S) {
 
 // First half: upload, transpose to structure-of-arrays, sequence the solve (all of it, or -- async -- up to the
 // point where the device finishes it on its own).
+struct ControlsInput {  // qilqr_solve_from_controls_host: the initial trajectory is rolled out on the device
+  const double *x0 = nullptr;        // [B][13]
+  const double *controls = nullptr;  // [Bc][N][4]
+  int Bc = 0;
+  double *out_controls = nullptr;
+};
 int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int Bd, const double *initial,
                      double *out_traj, double *out_k, double *out_K, double *cost_hist, int hist_cap,
-                     double *debug_traj, int debug_cap, qilqr_result_t *results, bool async) {
-  if (!S || !desired || !initial || !out_traj) return QILQR_ERR_INVALID_ARGUMENT;
+                     double *debug_traj, int debug_cap, qilqr_result_t *results, bool async,
+                     const ControlsInput *ci = nullptr) {
+  if (!S || !desired || (!initial && !ci) || (!out_traj && !(ci && ci->out_controls))) return QILQR_ERR_INVALID_ARGUMENT;
   if (B <= 0 || N <= 0 || (Bd != 1 && Bd != B)) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "bad batch/knots/desired_count");
   if (S->ctx.pending || S->host_call.pending) return fail(S, QILQR_ERR_INVALID_ARGUMENT, "a solve is still pending on this handle");
   QCUDA(S, cudaSetDevice(S->device));
@@ -1032,8 +1049,21 @@ int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int B
   QCUDA(S, S->desired_soa.ensure(sizeof(double) * size_t(N) * 17 * Bd));
   int rc = upload_traj(S, S->stage_b, Bd, N, desired, S->desired_soa.as<double>());
   if (rc) return rc;
-  rc = upload_traj(S, S->stage_a, B, N, initial, S->traj_soa.as<double>());
-  if (rc) return rc;
+  if (ci) {
+    // x0 and the nominal controls go up (13 + 4 N doubles per problem, or 13 when the controls are shared); the
+    // initial trajectory is their open-loop rollout, made where it is needed
+    QCUDA(S, S->stage_a.ensure(sizeof(double) * size_t(B) * N * 18));
+    QCUDA(S, S->stage_c.ensure(sizeof(double) * (size_t(B) * 13 + size_t(ci->Bc) * N * 4)));
+    double *d_x0 = S->stage_c.as<double>(), *d_u = d_x0 + size_t(B) * 13;
+    QCUDA(S, cudaMemcpyAsync(d_x0, ci->x0, sizeof(double) * size_t(B) * 13, cudaMemcpyHostToDevice, st_));
+    QCUDA(S, cudaMemcpyAsync(d_u, ci->controls, sizeof(double) * size_t(ci->Bc) * N * 4, cudaMemcpyHostToDevice, st_));
+    k_rollout_controls<<<blocks_for(B, 128), 128, 0, st_>>>(S->p, d_x0, d_u, ci->Bc, S->traj_soa.as<double>(), B, N);
+    if (out_traj) k_fill_time<<<blocks_for(B * N, 256), 256, 0, st_>>>(S->stage_a.as<double>(), B, N, S->p.dt);
+    S->launches += 2;
+  } else {
+    rc = upload_traj(S, S->stage_a, B, N, initial, S->traj_soa.as<double>());
+    if (rc) return rc;
+  }
   double *d_k = nullptr, *d_K = nullptr, *d_hist = nullptr, *d_debug = nullptr;
   if (out_k) { QCUDA(S, S->gk.ensure(sizeof(double) * size_t(N) * 4 * B)); d_k = S->gk.as<double>(); }
   if (out_K) { QCUDA(S, S->gK.ensure(sizeof(double) * size_t(N) * 48 * B)); d_K = S->gK.as<double>(); }
@@ -1063,6 +1093,7 @@ int solve_host_begin(qilqr_solver *S, int B, int N, const double *desired, int B
   hc.cost_hist = d_hist ? cost_hist : nullptr; hc.hist_cap = hist_cap;
   hc.debug_traj = want_debug ? debug_traj : nullptr; hc.debug_cap = debug_cap;
   hc.results = results;
+  hc.out_controls = ci ? ci->out_controls : nullptr;
   rc = solve_core(S, B, N, S->desired_soa.as<double>(), Bd, S->traj_soa.as<double>(), d_k, d_K, d_hist, hist_cap,
                   S->results_d.as<qilqr_result_t>(), d_debug, debug_cap, /*async_tail=*/true);
   S->dbg_time_aos = nullptr;
@@ -1085,6 +1116,22 @@ int qilqr_solve_host_begin(qilqr_solver_t *S, int B, int N, const double *desire
   if (!S) return QILQR_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lock(S->mu);
   return solve_host_begin(S, B, N, desired, Bd, initial, out_traj, nullptr, nullptr, nullptr, 0, nullptr, 0, results, true);
+}
+int qilqr_solve_from_controls_host(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *x0,
+                                   const double *controls, int control_count, double *out_traj, double *out_controls,
+                                   qilqr_result_t *results) {
+  if (!S || !x0 || !controls || (control_count != 1 && control_count != B)) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  ControlsInput ci{x0, controls, control_count, out_controls};
+  return solve_host_begin(S, B, N, desired, Bd, nullptr, out_traj, nullptr, nullptr, nullptr, 0, nullptr, 0, results, false, &ci);
+}
+int qilqr_solve_from_controls_host_begin(qilqr_solver_t *S, int B, int N, const double *desired, int Bd, const double *x0,
+                                         const double *controls, int control_count, double *out_traj,
+                                         double *out_controls, qilqr_result_t *results) {
+  if (!S || !x0 || !controls || (control_count != 1 && control_count != B)) return QILQR_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lock(S->mu);
+  ControlsInput ci{x0, controls, control_count, out_controls};
+  return solve_host_begin(S, B, N, desired, Bd, nullptr, out_traj, nullptr, nullptr, nullptr, 0, nullptr, 0, results, true, &ci);
 }
 int qilqr_solve_host_finish(qilqr_solver_t *S) {
   if (!S) return QILQR_ERR_INVALID_ARGUMENT;

@@ -1330,4 +1330,37 @@ k_rollout_constant(const __grid_constant__ DeviceParams p, const double *x0 /*[1
   }
 }
 
+// Open-loop rollout of array-of-structs initial states under given controls (the usual "nominal controls" initial
+// guess of an iLQR solver): x0 [B][13], controls [Bc][N][4] with Bc = 1 (shared) or B -> trajectory SoA [N][17][B].
+__global__ void __launch_bounds__(128)
+k_rollout_controls(const __grid_constant__ DeviceParams p, const double *x0_aos, const double *controls, int Bc,
+                   double *traj, int B, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[13];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) x[c] = x0_aos[size_t(b) * 13 + c];
+  const double *uc = controls + (Bc == 1 ? size_t(0) : size_t(b) * N * 4);
+  for (int i = 0; i < N; ++i) {
+    const double u[4] = {uc[4 * i], uc[4 * i + 1], uc[4 * i + 2], uc[4 * i + 3]};
+    store_point(traj, i, B, b, x, u);
+    gm::discrete_step_any(p, x, u);
+  }
+}
+// time_s column of an array-of-structs trajectory batch: t_i = i * dt
+__global__ void k_fill_time(double *aos, int B, int N, double dt) {
+  const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= size_t(B) * N) return;
+  aos[e * 18] = double(e % N) * dt;
+}
+// controls of a structure-of-arrays trajectory batch -> [B][N][4]
+__global__ void k_extract_controls(const double *soa, double *out, int B, int N) {
+  const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;  // over N * 4 * B, problem fastest
+  if (e >= size_t(B) * N * 4) return;
+  const int b = int(e % B);
+  const size_t r = e / B;  // i * 4 + j
+  const int i = int(r / 4), j = int(r % 4);
+  out[(size_t(b) * N + i) * 4 + j] = soa[(size_t(i) * 17 + 13 + j) * B + b];
+}
+
 }  // namespace qilqr

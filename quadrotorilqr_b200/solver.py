@@ -253,6 +253,27 @@ class BatchILQR:
     def solve_device_finish(self):
         self._check(_capi.lib().qilqr_solve_device_finish(self._h))
 
+    def solve_from_controls(self, x0, controls, desired, out_traj=None, out_controls=None, results=None,
+                            want_traj=True, want_controls=False, begin_only=False):
+        """``qilqr_solve_from_controls_host``: the initial guess is a control sequence (``controls [N, 4]`` shared or
+        ``[B, N, 4]``), the initial trajectory its open-loop rollout from ``x0 [B, 13]`` on the device."""
+        x0 = x0 if not isinstance(x0, np.ndarray) else _f64(x0)
+        B = int(x0.shape[0])
+        controls = controls if not isinstance(controls, np.ndarray) else _f64(controls)
+        Bc = 1 if controls.ndim == 2 else int(controls.shape[0])
+        N = int(controls.shape[-2])
+        Bd = 1 if desired.ndim == 2 else int(desired.shape[0])
+        if out_traj is None and want_traj:
+            out_traj = np.empty((B, N, 18))
+        if out_controls is None and want_controls:
+            out_controls = np.empty((B, N, 4))
+        res = results if results is not None else np.zeros(B, dtype=RESULT_DTYPE)
+        fn = (_capi.lib().qilqr_solve_from_controls_host_begin if begin_only
+              else _capi.lib().qilqr_solve_from_controls_host)
+        self._check(fn(self._h, C.c_int(B), C.c_int(N), _ptr(desired), C.c_int(Bd), _ptr(x0), _ptr(controls),
+                       C.c_int(Bc), _ptr(out_traj), _ptr(out_controls), _ptr(res)))
+        return dict(traj=out_traj, controls=out_controls, results=res)
+
     def solve_host_buffers(self, initial, desired, out_traj, results):
         """Zero-allocation variant for (pinned) host buffers: numpy arrays or CPU torch tensors."""
         B, N = int(initial.shape[0]), int(initial.shape[1])

@@ -104,3 +104,28 @@ def test_concurrent_handles_do_not_interfere():
         t.join()
     for j in range(3):
         assert np.array_equal(out[j]["traj"], ref[j]["traj"]) and np.array_equal(out[j]["results"], ref[j]["results"])
+
+
+def test_solve_from_controls_equals_rollout_then_solve():
+    """qilqr_solve_from_controls_host: x0 + nominal controls in, the initial trajectory rolled out on the device --
+    bit-identical to forward_sim (zero gains) followed by solve; shared and per-problem control sequences;
+    trajectories and / or controls out."""
+    from quadrotorilqr_b200 import problems
+
+    model, opts = problems.hover_model(), problems.default_options(False)
+    s = make_solver(model, opts)
+    B, N = 130, 40
+    desired = problems.hover_desired_trajectory(N, model["dt_s"], model["mass_kg"], model["g_mpss"])
+    x0 = problems.hover_initial_states(B, seed=9)
+    rng = np.random.default_rng(1)
+    for controls in (np.tile(desired[0, 14:18], (N, 1)), desired[0, 14:18] + rng.uniform(-0.2, 0.2, (B, N, 4))):
+        seedtraj = problems.constant_state_trajectory(x0, N, model["dt_s"], desired[0, 14:18])
+        seedtraj[:, :, 14:18] = controls
+        initial = s.forward_sim(seedtraj, np.zeros((B, N, 4)), np.zeros((B, N, 48)))
+        want = s.solve(initial, desired)
+        got = s.solve_from_controls(x0, controls, desired, want_controls=True)
+        assert np.array_equal(got["results"], want["results"])
+        assert np.array_equal(got["traj"], want["traj"])            # time_s = knot * dt_s as well
+        assert np.array_equal(got["controls"], want["traj"][:, :, 14:18])
+        only_u = s.solve_from_controls(x0, controls, desired, want_traj=False, want_controls=True)
+        assert only_u["traj"] is None and np.array_equal(only_u["controls"], got["controls"])
