@@ -27,8 +27,15 @@
 #ifndef QILQR_H_
 #define QILQR_H_
 
+#ifdef __CUDACC_RTC__ /* compiled by NVRTC as part of a user-model translation unit: no host headers */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -123,6 +130,21 @@ int qilqr_set_options(qilqr_solver_t *solver, const qilqr_options_t *options);
  * 0 (the default) is the reference's QuadrotorModel on the quadrotor-specific kernels. */
 enum { QILQR_MODEL_REFERENCE = 0, QILQR_MODEL_RK4 = 1, QILQR_MODEL_CORIOLIS = 2, QILQR_MODEL_GENERIC = 4 };
 int qilqr_set_model_variant(qilqr_solver_t *solver, int model_flags);
+/* A USER-SUPPLIED MODEL behind the ModelT concept (ilqr.hh:25-44, 110-112: the solver sees a model only through
+ * discrete_dynamics(x, u, dt, diffs*)).  `cuda_source` is CUDA C++ that defines
+ *
+ *   extern "C" __device__ void qilqr_user_discrete_dynamics(const double *params, const double *x, const double *u,
+ *                                                           double dt, double *x_next, double *J_x, double *J_u);
+ *
+ * (x, x_next: 13 doubles; u: 4; J_x: 12x12 and J_u: 12x4 row-major, nullptr when only the step is wanted)
+ * on the state manifold of QuadrotorModel::State (SE(3) x R^6; Jacobians with respect to right-plus perturbations,
+ * as QuadrotorModel::DynamicsDifferentials, quadrotor_model.hh:42-45).  It is compiled at run time (NVRTC, sm_100a,
+ * -fmad=false) together with the model-agnostic kernels -- dense linearisation, rollout -- and may use this
+ * library's device functions (so3_exp, se3_plus_blocks, quat_compose, ...: qilqr_device.cuh is included ahead of
+ * it).  `params` (at most 64 doubles) is handed to every call.  Every later solve / forward_sim / backwards_pass of
+ * this handle uses the model; compile errors come back through qilqr_last_error_message.  Needs libnvrtc.so.12 and
+ * the csrc/ directory next to the shared library (or QILQR_CSRC_DIR). */
+int qilqr_set_user_model(qilqr_solver_t *solver, const char *cuda_source, const double *params, int n_params);
 const char *qilqr_error_string(int err);
 /* How this build rounds: "production: explicit fused multiply-adds, reciprocal multiplies" or
  * "strict: no fused multiply-adds, true divisions (-DQILQR_STRICT)"; both are compiled with -fmad=false. */

@@ -97,7 +97,7 @@ EXPORTED_SYMBOLS = [
     "qilqr_set_model_variant", "qilqr_build_info", "qilqr_solve_host_begin", "qilqr_solve_host_finish",
     "qilqr_solve_device_begin", "qilqr_solve_device_finish", "qilqr_set_debug_sampling",
     "qilqr_read_debug_samples_host", "qilqr_last_cost_history_host", "qilqr_solve_from_controls_host",
-    "qilqr_solve_from_controls_host_begin",
+    "qilqr_solve_from_controls_host_begin", "qilqr_set_user_model",
 ]
 
 MODEL_REFERENCE = 0

@@ -168,6 +168,8 @@ struct QuadrotorModel {
     if (qilqr_check_model(&m) != QILQR_OK)
       throw std::runtime_error("Inertia matrix is not positive definite!");  // quadrotor_model.cc:21-24
   }
+  // hook run on every solver handle created for this model (see UserModel)
+  void configure(qilqr_solver_t *) const {}
   qilqr_model_t c_model() const {
     qilqr_model_t m{};
     m.mass_kg = mass_kg_;
@@ -231,6 +233,20 @@ struct QuadrotorModelVariant : QuadrotorModel {
       : QuadrotorModel(mass_kg, inertia, arm_length_m, torque_to_thrust_ratio_m, g_mpss) {
     model_flags_ = (rk4 ? QILQR_MODEL_RK4 : 0) | (coriolis ? QILQR_MODEL_CORIOLIS : 0);
     if (!model_flags_) model_flags_ = QILQR_MODEL_GENERIC;  // the reference dynamics on the generic kernels
+  }
+};
+
+// A model SUPPLIED BY THE CALLER behind the ModelT concept (ilqr.hh:25-44): CUDA C++ source defining
+// qilqr_user_discrete_dynamics (include/qilqr.h, qilqr_set_user_model), compiled at run time and run on the
+// model-agnostic kernels.  `base` provides the State / Control types and the constants the cost's minus() needs;
+// its own dynamics are not used by ILQR<UserModel>::solve / forward_sim / backwards_pass.
+struct UserModel : QuadrotorModel {
+  std::string cuda_source_;
+  std::vector<double> params_;
+  UserModel(const QuadrotorModel &base, std::string cuda_source, std::vector<double> params)
+      : QuadrotorModel(base), cuda_source_(std::move(cuda_source)), params_(std::move(params)) {}
+  void configure(qilqr_solver_t *h) const {
+    check(qilqr_set_user_model(h, cuda_source_.c_str(), params_.empty() ? nullptr : params_.data(), int(params_.size())), h);
   }
 };
 
@@ -440,7 +456,9 @@ struct ILQR {  // ilqr.hh:25-206
       : model_(std::move(model)), cost_function_(std::move(cost_function)), dt_s_(dt_s), options_(options),
         h_(std::make_shared<Handle>(model_.c_model(), cost_function_.Q(), cost_function_.R(), dt_s, options, 0,
                                     model_.model_flags_)),
-        desired_(flatten<ModelT>(cost_function_.desired_trajectory())) {}
+        desired_(flatten<ModelT>(cost_function_.desired_trajectory())) {
+    model_.configure(h_->h);
+  }
 
   // ilqr.hh:53-87
   std::pair<Trajectory<ModelT>, ILQRDebug<ModelT>> solve(const Trajectory<ModelT> &initial_traj) const {

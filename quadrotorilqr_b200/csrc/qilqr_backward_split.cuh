@@ -15,7 +15,9 @@
 // of the records through HBM (800 B per problem-knot).
 // =============================================================================
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #include "qilqr_backward_g4.cuh"
 

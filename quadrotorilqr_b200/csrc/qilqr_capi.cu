@@ -6,6 +6,7 @@
 // CUDA kernels or fails.
 // =============================================================================
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -131,6 +132,11 @@ struct qilqr_solver {
   DeviceBuffer dbg_sample, dbg_traj, dbg_iters, dbg_costs, dbg_count;
   int dbg_S = 0, dbg_ring = 0, dbg_every = 0, dbg_N = 0;  // dbg_S == 0: sampling off; dbg_N: knots of the captured solve
   const double *dbg_time_aos = nullptr;                    // host path: the input AoS on the device (time_s column)
+  // user-supplied model compiled at run time (qilqr_set_user_model): the generic kernels around the caller's
+  // discrete_dynamics device function
+  cudaLibrary_t user_lib = nullptr;
+  cudaKernel_t user_linearise = nullptr, user_rollout = nullptr;
+  bool user_model = false;
   SolveCtx ctx;                   // a solve whose tail is still running on the device (begin / finish API)
   HostCall host_call;
   std::mutex mu;                  // one call at a time per handle (the workspace is shared by every entry point)
@@ -372,14 +378,25 @@ int launch_dense(qilqr_solver *S, const BackwardArgs &ba) {
   if (S->rec_d.ensure(need) != cudaSuccess) return QILQR_ERR_OUT_OF_MEMORY;
   const size_t smem = sizeof(double) * dn::smem_doubles();
   const size_t threads = size_t(n8) * ba.pr.N;
-  k_linearise_dense<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  if (S->user_model) {
+    double *rec = S->rec_d.as<double>();
+    void *args[] = {const_cast<DeviceParams *>(&S->p), const_cast<BackwardArgs *>(&ba), &rec};
+    if (cudaLaunchKernel(reinterpret_cast<const void *>(S->user_linearise), dim3(unsigned((threads + 127) / 128)), dim3(128),
+                         args, 0, S->cur) != cudaSuccess)
+      return QILQR_ERR_CUDA;
+  } else {
+    k_linearise_dense<<<unsigned((threads + 127) / 128), 128, 0, S->cur>>>(S->p, ba, S->rec_d.as<double>());
+  }
   k_riccati_dense<<<n8 / 8, 32, smem, S->cur>>>(S->p, ba, S->rec_d.as<double>());
   ++S->launches;
   return QILQR_OK;
 }
 // forward_sim (+ cost, + line-search bookkeeping) with the dynamics of the configured model
 void launch_rollout(qilqr_solver *S, const RolloutArgs &ra, int threads, cudaStream_t st) {
-  if (S->generic_path) k_rollout<true><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
+  if (S->user_model) {
+    void *args[] = {const_cast<DeviceParams *>(&S->p), const_cast<RolloutArgs *>(&ra)};
+    cudaLaunchKernel(reinterpret_cast<const void *>(S->user_rollout), dim3(blocks_for(threads, 128)), dim3(128), args, 0, st);
+  } else if (S->generic_path) k_rollout<true><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
   // (the parallel step-size rounds stay on the one-thread-per-problem kernel; the two kernels are bit-identical)
   else if (S->rollout_ws && ra.mode != MODE_WIDE && threads <= S->ws_threshold) k_rollout_ws<<<blocks_for(threads, 32), 96, 0, st>>>(S->p, ra);
   else k_rollout<false><<<blocks_for(threads, 128), 128, 0, st>>>(S->p, ra);
@@ -812,6 +829,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
                           &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count, &S->stage_d})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
+  if (S->user_lib) cudaLibraryUnload(S->user_lib);
   if (S->h_counts) cudaFreeHost(S->h_counts);
   if (S->h_totals) cudaFreeHost(S->h_totals);
   if (S->ev_switch) cudaEventDestroy(S->ev_switch);
@@ -826,8 +844,114 @@ int qilqr_set_options(qilqr_solver_t *S, const qilqr_options_t *options) {
   apply_options(S);
   return QILQR_OK;
 }
+// ---- user-supplied model: NVRTC ---------------------------------------------------------------
+namespace {
+struct Nvrtc {  // libnvrtc, loaded on first use (the library itself does not link against it)
+  void *lib = nullptr;
+  int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*DestroyProgram)(void **) = nullptr;
+  int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+  int (*AddNameExpression)(void *, const char *) = nullptr;
+  int (*GetLoweredName)(void *, const char *, const char **) = nullptr;
+  int (*GetCUBINSize)(void *, size_t *) = nullptr;
+  int (*GetCUBIN)(void *, char *) = nullptr;
+  int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+  int (*GetProgramLog)(void *, char *) = nullptr;
+  bool ok = false;
+  Nvrtc() {
+    for (const char *name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (lib) break;
+    }
+    if (!lib) return;
+#define QSYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(lib, sym)); if (!field) return
+    QSYM(CreateProgram, "nvrtcCreateProgram");
+    QSYM(DestroyProgram, "nvrtcDestroyProgram");
+    QSYM(CompileProgram, "nvrtcCompileProgram");
+    QSYM(AddNameExpression, "nvrtcAddNameExpression");
+    QSYM(GetLoweredName, "nvrtcGetLoweredName");
+    QSYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    QSYM(GetCUBIN, "nvrtcGetCUBIN");
+    QSYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    QSYM(GetProgramLog, "nvrtcGetProgramLog");
+#undef QSYM
+    ok = true;
+  }
+};
+std::string source_dir() {  // <dir of this shared library>/csrc, or QILQR_CSRC_DIR
+  if (const char *e = std::getenv("QILQR_CSRC_DIR")) return e;
+  Dl_info info;
+  if (dladdr(reinterpret_cast<const void *>(&qilqr_build_info), &info) && info.dli_fname) {
+    std::string path = info.dli_fname;
+    const size_t slash = path.rfind('/');
+    return (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/csrc";
+  }
+  return "csrc";
+}
+}  // namespace
+
+int qilqr_set_user_model(qilqr_solver_t *S, const char *cuda_source, const double *params, int n_params) {
+  if (!S || !cuda_source || n_params < 0 || n_params > 64 || (n_params && !params)) return QILQR_ERR_INVALID_ARGUMENT;
+  QENTER(S);
+  static Nvrtc nv;
+  if (!nv.ok) return fail(S, QILQR_ERR_CUDA, "libnvrtc.so.12 could not be loaded: a user-supplied model needs the CUDA run-time compiler");
+  QCUDA(S, cudaSetDevice(S->device));
+  const std::string dir = source_dir();
+  // the caller's function sits between the device library (which it may use) and the generic kernels (which call it)
+  const std::string unit = std::string("#define QILQR_USER_MODEL_TU 1\n#include \"qilqr_device.cuh\"\n#line 1 \"user_model.cu\"\n") +
+                           cuda_source + "\n#include \"qilqr_backward_dense.cuh\"\n";
+  void *prog = nullptr;
+  if (nv.CreateProgram(&prog, unit.c_str(), "qilqr_user_model_unit.cu", 0, nullptr, nullptr) != 0)
+    return fail(S, QILQR_ERR_CUDA, "nvrtcCreateProgram failed");
+  const std::string inc1 = "-I" + dir, inc2 = "-I" + dir + "/../../include";
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-default-device", inc1.c_str(), inc2.c_str()};
+  const char *n_lin = "qilqr::k_linearise_dense", *n_roll = "qilqr::k_rollout<true>";
+  nv.AddNameExpression(prog, n_lin);
+  nv.AddNameExpression(prog, n_roll);
+  const int rc = nv.CompileProgram(prog, int(sizeof(opts) / sizeof(opts[0])), opts);
+  if (rc != 0) {
+    size_t n = 0;
+    nv.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nv.GetProgramLog(prog, &log[0]);
+    nv.DestroyProgram(&prog);
+    S->last_error = "the user model did not compile:\n" + log;
+    return QILQR_ERR_INVALID_ARGUMENT;
+  }
+  const char *l_lin = nullptr, *l_roll = nullptr;
+  size_t nb = 0;
+  if (nv.GetLoweredName(prog, n_lin, &l_lin) != 0 || nv.GetLoweredName(prog, n_roll, &l_roll) != 0 ||
+      nv.GetCUBINSize(prog, &nb) != 0 || nb == 0) {
+    nv.DestroyProgram(&prog);
+    return fail(S, QILQR_ERR_CUDA, "NVRTC produced no code for the user-model kernels");
+  }
+  std::vector<char> cubin(nb);
+  nv.GetCUBIN(prog, cubin.data());
+  const std::string s_lin = l_lin, s_roll = l_roll;
+  nv.DestroyProgram(&prog);
+  cudaLibrary_t lib = nullptr;
+  QCUDA(S, cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  cudaKernel_t k_lin = nullptr, k_roll = nullptr;
+  void *d_params = nullptr;
+  size_t param_bytes = 0;
+  if (cudaLibraryGetKernel(&k_lin, lib, s_lin.c_str()) != cudaSuccess || cudaLibraryGetKernel(&k_roll, lib, s_roll.c_str()) != cudaSuccess ||
+      cudaLibraryGetGlobal(&d_params, &param_bytes, lib, "_ZN5qilqr11user_paramsE") != cudaSuccess) {
+    cudaLibraryUnload(lib);
+    return fail(S, QILQR_ERR_CUDA, "the user-model kernels were not found in the compiled unit");
+  }
+  if (n_params) QCUDA(S, cudaMemcpy(d_params, params, sizeof(double) * size_t(n_params), cudaMemcpyHostToDevice));
+  if (S->user_lib) cudaLibraryUnload(S->user_lib);
+  S->user_lib = lib;
+  S->user_linearise = k_lin;
+  S->user_rollout = k_roll;
+  S->user_model = true;
+  S->generic_path = true;
+  return QILQR_OK;
+}
+
 int qilqr_set_model_variant(qilqr_solver_t *S, int model_flags) {
   if (!S || model_flags < 0 || model_flags > 7) return QILQR_ERR_INVALID_ARGUMENT;
+  S->user_model = false;
   S->p.integrator = (model_flags & QILQR_MODEL_RK4) ? 1 : 0;
   S->p.coriolis = (model_flags & QILQR_MODEL_CORIOLIS) ? 1 : 0;
   S->generic_path = model_flags != 0;

@@ -12,8 +12,10 @@
 // Storage: quaternion (x,y,z,w); 3x3 matrices row-major double[9].
 // =============================================================================
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <math.h>
+#endif
 
 #define QD __device__ __forceinline__
 

@@ -633,6 +633,7 @@ QD void cost_derivatives(const DeviceParams &p, const double *dx, const double *
   }
 }
 
+#ifndef QILQR_USER_MODEL_TU  // (not needed in a run-time compiled user-model unit)
 __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ DeviceParams p, const __grid_constant__ BackwardArgs a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.n) return;
@@ -860,6 +861,8 @@ __global__ void __launch_bounds__(64) k_backward_t1(const __grid_constant__ Devi
 
   backward_finish(p, a, b, QuTk, kTQuuk);
 }
+
+#endif  // QILQR_USER_MODEL_TU
 
 // ---------------------------------------------------------------------------
 // Parallel line search: after a MODE_WIDE round, pick the FIRST (largest) step size that passes the

@@ -57,6 +57,37 @@ QD void euler_state(const double *x /*13*/, const double *k /*12*/, double dt, d
   for (int i = 0; i < 6; ++i) xn[7 + i] = QFMA(dt, k[6 + i], x[7 + i]);
 }
 
+#ifdef QILQR_USER_MODEL_TU
+}  // namespace gm
+}  // namespace qilqr
+// ---------------------------------------------------------------------------
+// USER-SUPPLIED MODEL (qilqr_set_user_model): this translation unit is compiled at run time by NVRTC around a
+// device function the caller provides -- the ModelT concept of ilqr.hh:25-44 on the state manifold SE(3) x R^6:
+//   x, x_next: 13 doubles (t, q(x,y,z,w), body velocity); u: 4; J_x: 12x12 row-major, J_u: 12x4 row-major,
+//   derivatives with respect to right-plus perturbations of the state (as QuadrotorModel::DynamicsDifferentials);
+//   J_x / J_u are nullptr when only the step is wanted; params: the doubles passed to qilqr_set_user_model.
+// ---------------------------------------------------------------------------
+extern "C" __device__ void qilqr_user_discrete_dynamics(const double *params, const double *x, const double *u,
+                                                        double dt, double *x_next, double *J_x, double *J_u);
+namespace qilqr {
+__device__ double user_params[64];
+namespace gm {
+QD void discrete_step_any(const DeviceParams &p, double *x /*13*/, const double *u) {
+  double xn[13];
+  qilqr_user_discrete_dynamics(user_params, x, u, p.dt, xn, nullptr, nullptr);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) x[i] = xn[i];
+}
+QD void discrete_with_jacobians(const DeviceParams &p, const double *x, const double *u, double *xn, double *A,
+                                double *B, int stride) {
+  double Jx[144], Ju[48];
+  qilqr_user_discrete_dynamics(user_params, x, u, p.dt, xn, A ? Jx : nullptr, B ? Ju : nullptr);
+  if (A)
+    for (int e = 0; e < 144; ++e) A[e * stride] = Jx[e];
+  if (B)
+    for (int e = 0; e < 48; ++e) B[e * stride] = Ju[e];
+}
+#else
 // discrete_dynamics without derivatives for any variant; x is advanced in place
 QD void discrete_step_any(const DeviceParams &p, double *x /*13*/, const double *u) {
   if (!p.integrator) {
@@ -342,6 +373,7 @@ QD void cont_jx_dense(const DeviceParams &p, const ContBlocks &F, double *J) {
       }
     }
 }
+#endif  // QILQR_USER_MODEL_TU
 
 }  // namespace gm
 }  // namespace qilqr

@@ -120,6 +120,15 @@ class BatchILQR:
         o = _options_struct(options)
         self._check(_capi.lib().qilqr_set_options(self._h, C.byref(o)))
 
+    def set_user_model(self, cuda_source: str, params=()):
+        """``qilqr_set_user_model``: run every later call of this solver with the caller's ``discrete_dynamics``
+        (CUDA C++ defining ``qilqr_user_discrete_dynamics``, compiled at run time) on the model-agnostic kernels."""
+        par = _f64(np.asarray(params, dtype=np.float64).ravel())
+        rc = _capi.lib().qilqr_set_user_model(self._h, C.c_char_p(cuda_source.encode()), _ptr(par) if par.size else None,
+                                              C.c_int(par.size))
+        if rc:
+            raise QilqrError(rc, _capi.lib().qilqr_last_error_message(self._h).decode())
+
     def set_profiling(self, enabled: bool):
         self._check(_capi.lib().qilqr_set_profiling(self._h, C.c_int(int(enabled))))
 

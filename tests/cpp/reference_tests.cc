@@ -151,6 +151,37 @@ static void SecondModelSolveFindsOptimalTrajectory() {
     }
   }
 }
+// ILQR<ModelT> with a model SUPPLIED BY THE CALLER (examples/user_model_drag.cu, compiled at run time): the same
+// fixture problem; with c_d = 0 the optimum is the identity trajectory as for the reference model.
+static void UserModelSolveFindsOptimalTrajectory() {
+  std::string path = std::string(QILQR_REPO_ROOT) + "/examples/user_model_drag.cu", src;
+  if (FILE *f = std::fopen(path.c_str(), "rb")) {
+    char buf[4096];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) src.append(buf, n);
+    std::fclose(f);
+  }
+  EXPECT_TRUE(!src.empty());
+  using USolver = ILQR<UserModel>;
+  using UCost = CostFunction<UserModel>;
+  const QuadrotorModel base{mass_kg, Identity3(), 1.0, 1.0, 0.0};
+  const UserModel model{base, src, {mass_kg, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0}};  // g = 0 as in the fixture
+  Trajectory<UserModel> identity;
+  for (const auto &pt : create_identity_traj(3, 0.1)) identity.push_back({pt.time_s, pt.state, pt.control});
+  USolver ilqr{model, UCost{Identity12(), Identity4(), identity}, 0.1,
+               ILQROptions{LineSearchParams{0.5, 0.5, 10}, ConvergenceCriteria{1e-12, 1e-12, 100}}};
+  USolver::ControlUpdate u{};
+  u.ff_update = {100, 1, 100, 1};
+  const USolver::ControlUpdateTrajectory upd(3, u);
+  const auto initial = ilqr.forward_sim(identity, upd);
+  EXPECT_TRUE(ilqr.cost_trajectory(initial) > 1.0);
+  const auto [opt, debug] = ilqr.solve(initial);
+  for (size_t i = 0; i < opt.size(); ++i) {
+    const auto d = (opt[i].state - identity[i].state).coeffs();
+    for (int j = 0; j < 12; ++j) EXPECT_NEAR(d[j], 0.0, 1e-6);
+    for (int j = 0; j < 4; ++j) EXPECT_NEAR(opt[i].control[j], 0.0, 1e-6);
+  }
+}
 static void DiscreteDynamicsKnownAnswers() {  // quadrotor_model_test.cc:94-143
   QuadrotorModel quad{mass_kg, Identity3(), 1.0, 1.0};
   State x = create_identity_state();
@@ -248,6 +279,7 @@ int main() {
       {"ILQRFixture.LineSearchFindsStepSizeThatReducesCost", LineSearchFindsStepSizeThatReducesCost},
       {"ILQRFixture.SolveFindsOptimalTrajectory", SolveFindsOptimalTrajectory},
       {"SecondModel.SolveFindsOptimalTrajectory", SecondModelSolveFindsOptimalTrajectory},
+      {"UserModel.SolveFindsOptimalTrajectory", UserModelSolveFindsOptimalTrajectory},
       {"QuadrotorModelTest.DiscreteDynamicsKnownAnswers", DiscreteDynamicsKnownAnswers},
       {"StateTangentAndExceptions", StateTangentAndExceptions},
       {"EqualityOperators", EqualityOperators},

@@ -16,7 +16,7 @@ def build_exe():
 
     _capi.build()
     lib_dir = os.path.dirname(_capi.LIB_PATH)
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, SRC, "-L" + lib_dir, "-lqilqr_b200",
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", f'-DQILQR_REPO_ROOT="{ROOT}"', "-o", EXE, SRC, "-L" + lib_dir, "-lqilqr_b200",
            "-Wl,-rpath," + lib_dir, "-L/usr/local/cuda/lib64", "-lcudart"]
     subprocess.check_call(cmd)
     return EXE
@@ -32,4 +32,4 @@ def test_reference_gtests_pass_through_the_cpp_mirror():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("[  OK  ]") == 11
+    assert out.stdout.count("[  OK  ]") == 12
