@@ -19,6 +19,7 @@
 //     skipped, a repeated occurrence of a singular message field merges into the previous one
 // =============================================================================
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <optional>
@@ -290,6 +291,11 @@ inline qilqr::SE3 from_proto(const SE3 &p) {
   qilqr::SE3 X;
   X.translation = from_proto(p.translation.value_or(Vec3{}));
   const Vec4 q = p.rotation.value_or(SO3{}).quaternion.value_or(Vec4{});
+  // the reference builds a manif::SO3d here (trajectory_to_proto.cc:76-83), which rejects a quaternion that is not
+  // normalised -- e.g. the all-zero one of a message without a rotation.  (manif's own tolerance is its eps on
+  // | |q|^2 - 1 |; this one is deliberately looser so that accumulated rounding is not rejected.)
+  const double n2 = q.c0 * q.c0 + q.c1 * q.c1 + q.c2 * q.c2 + q.c3 * q.c3;
+  if (!(std::fabs(n2 - 1.0) <= 1e-9)) throw std::invalid_argument("SO3 assigned data not normalized !");
   X.quaternion = {q.c1, q.c2, q.c3, q.c0};
   return X;
 }

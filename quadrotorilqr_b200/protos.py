@@ -86,6 +86,10 @@ def trajectory_from_proto(msg) -> np.ndarray:
     for i, pt in enumerate(msg.points):
         t, q, v, u = (pt.state.inertial_from_body.translation, pt.state.inertial_from_body.rotation.quaternion,
                       pt.state.body_velocity, pt.control)
+        # the reference builds a manif::SO3d here (trajectory_to_proto.cc:76-83), which rejects a quaternion that is
+        # not normalised -- e.g. the all-zero one of a point without a rotation (tolerance looser than manif's eps)
+        if not abs(q.c0 * q.c0 + q.c1 * q.c1 + q.c2 * q.c2 + q.c3 * q.c3 - 1.0) <= 1e-9:
+            raise ValueError(f"SO3 assigned data not normalized ! (trajectory point {i})")
         out[i] = [pt.time_s, t.c0, t.c1, t.c2, q.c1, q.c2, q.c3, q.c0, v.c0, v.c1, v.c2, v.c3, v.c4, v.c5,
                   u.c0, u.c1, u.c2, u.c3]
     return out

@@ -31,13 +31,17 @@ class QuadrotorILQR:
             raise IndexError("vector::_M_range_check")  # std::out_of_range, cost.hh:39-40
         if n == 0:
             raise ValueError("empty trajectory")  # undefined behaviour in the reference (ilqr.hh:156)
-        r = self._solver.solve(init[None], self._desired[:n],
-                               hist_cap=int(np.ceil(self._options.convergence_criteria.max_iters)) + 1,
-                               want_debug=self._options.populate_debug)
+        # `for (int i = 0; i < max_iters; ++i)` with max_iters a double (ilqr.hh:58): a NaN or non-positive bound runs
+        # no iteration; the history needs one entry per completed iteration
+        mi = self._options.convergence_criteria.max_iters
+        cap = int(min(np.ceil(mi), 1 << 20)) + 1 if (mi == mi and mi > 0) else 1
+        r = self._solver.solve(init[None], self._desired[:n], hist_cap=cap,
+                               want_debug=self._options.populate_debug and cap > 1)
         res = r["results"][0]
         if res["status"] in (_capi.STATUS_LINE_SEARCH_FAILED, _capi.STATUS_NONFINITE):  # std::runtime_error, ilqr.hh:191-193
+            why = " (the candidate costs were not finite)" if res["status"] == _capi.STATUS_NONFINITE else ""
             raise RuntimeError("Reached maximum number of line search iterations, "
-                               f"{self._options.line_search_params.max_iters}\n")
-        nd = int(res["num_debug"]) if self._options.populate_debug else 0
+                               f"{self._options.line_search_params.max_iters}{why}\n")
+        nd = int(res["num_debug"]) if (self._options.populate_debug and r["debug"] is not None) else 0
         debug = protos.debug_to_proto(r["debug"][0][:nd] if nd else [], r["cost_history"][0][:nd] if nd else [])
         return protos.trajectory_to_proto(r["traj"][0]), debug

@@ -50,6 +50,7 @@ def test_options_and_debug_round_trip():
     o = problems.default_options(True)
     assert protos.options_from_proto(protos.options_to_proto(o)) == o
     trajs = [problems.default_desired_trajectory() * s for s in (1.0, 0.5)]
+    trajs[1][:, 4:8] = trajs[0][:, 4:8]  # (quaternions stay normalised: the converters reject others, as manif does)
     msg = protos.debug_to_proto(trajs, [3.0, 1.5])
     tr, costs = protos.debug_from_proto(protos.ilqr_debug_pb2.QuadrotorILQRDebug.FromString(msg.SerializeToString()))
     assert costs == [3.0, 1.5] and all(np.array_equal(a, b) for a, b in zip(tr, trajs))
@@ -83,3 +84,21 @@ def test_reference_demo_flow_through_the_binding(O):
     with pytest.raises(IndexError):  # cost.hh:39-40
         QuadrotorILQR(1.0, np.eye(3), 1.0, 0.0, 9.81, Q, np.eye(4), protos.trajectory_to_proto(desired[:10]), 0.1,
                       options).solve(desired_traj)
+
+
+def test_unnormalised_quaternions_are_rejected():
+    """from_proto builds a manif::SO3d in the reference (trajectory_to_proto.cc:76-83), which rejects a quaternion
+    that is not normalised -- e.g. the all-zero one of a message without a rotation."""
+    from quadrotorilqr_b200 import problems, protos
+
+    good = protos.trajectory_to_proto(problems.default_desired_trajectory())
+    protos.trajectory_from_proto(good)
+    bad = protos.trajectory_pb2.QuadrotorTrajectory()
+    bad.points.add().time_s = 1.0  # no state at all: quaternion (0, 0, 0, 0)
+    with pytest.raises(ValueError, match="not normalized"):
+        protos.trajectory_from_proto(bad)
+    scaled = protos.trajectory_pb2.QuadrotorTrajectory()
+    scaled.CopyFrom(good)
+    scaled.points[3].state.inertial_from_body.rotation.quaternion.c0 *= 1.001
+    with pytest.raises(ValueError, match="not normalized"):
+        protos.trajectory_from_proto(scaled)
