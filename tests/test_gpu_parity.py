@@ -14,12 +14,26 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-def assert_close(a, b, rtol=RTOL, what=""):
+FLOOR = 1e-3  # entries below FLOOR * (the array's largest magnitude) are compared as if they had that magnitude
+
+
+def assert_close(a, b, rtol=RTOL, what="", floor=FLOOR):
+    """ELEMENT-WISE relative comparison: |a_ij - b_ij| <= rtol * max(|b_ij|, floor * max|b|, tiny).
+
+    Small gain entries are thus held to rtol relative to themselves down to 1e-3 of the array's scale (below that
+    an entry is the result of cancellation and only its absolute error is meaningful).  rtol = 0 demands equality."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
-    scale = max(1.0, float(np.max(np.abs(b)))) if b.size else 1.0
-    err = float(np.max(np.abs(a - b))) if b.size else 0.0
-    assert err <= rtol * scale, f"{what}: max abs err {err:.3e} > {rtol:g} * {scale:.3e}"
+    if not b.size:
+        return
+    scale = max(1.0, float(np.max(np.abs(b))))
+    tol = rtol * np.maximum(np.abs(b), floor * scale)
+    err = np.abs(a - b)
+    bad = err > tol
+    if np.any(bad):
+        i = np.unravel_index(np.argmax(err / np.maximum(tol, 1e-300)), err.shape) if err.ndim else ()
+        raise AssertionError(f"{what}: element {i}: |{a[i]!r} - {b[i]!r}| = {err[i]:.3e} > {tol[i]:.3e} "
+                             f"(rtol {rtol:g}, array scale {scale:.3e})")
 
 
 def random_states(O, n, seed, big=False):
@@ -230,8 +244,8 @@ def test_pieces_match_oracle_on_hover_batch(O):
         assert_close(K[b], Ko, what="K")
         assert_close(QuTk[b], a, what="QuTk")
         assert_close(kTQuuk[b], c, what="kTQuuk")
-        assert_close(new[b], O.forward_sim(cfg, desired, initial[b], ko, Ko, 1.0), rtol=1e-8, what="fwd 1.0")
-        assert_close(half[b], O.forward_sim(cfg, desired, initial[b], ko, Ko, 0.5), rtol=1e-8, what="fwd 0.5")
+        assert_close(new[b], O.forward_sim(cfg, desired, initial[b], ko, Ko, 1.0), what="fwd 1.0")
+        assert_close(half[b], O.forward_sim(cfg, desired, initial[b], ko, Ko, 0.5), what="fwd 0.5")
 
 
 def check_solve_against_oracle(O, s, cfg, desired, initial, hist_cap=100):
@@ -443,7 +457,7 @@ def test_long_horizon_figure_eight(O):
     assert np.array_equal(r["results"]["rollouts"], o["rollouts"])
     assert np.all(np.isin(o["status"], [1, 2])) and o["backward_passes"].max() < 30
     for b in range(B):
-        assert_close(r["traj"][b], o["traj"][b], rtol=1e-7, what="long-horizon traj")
+        assert_close(r["traj"][b], o["traj"][b], what="long-horizon traj")  # measured over 4096 problems: 7.5e-15
         assert_close(r["cost_history"][b], o["cost_history"][b], rtol=1e-9, what="long-horizon cost history")
 
 
