@@ -32,8 +32,13 @@ namespace qilqr {
 
 namespace g4 {
 constexpr int R_RE = 0, R_TE = 9, R_DJR = 18, R_DQB = 27, R_GZ = 36, R_WD = 39, R_CX = 48, R_CU = 60, R_CPP = 64;
-constexpr int R_CPV = 100, R_CVP = 136;  // only in records of a Q with pose/velocity coupling (172 doubles)
-constexpr int REC = 101;  // = 5 (mod 16)
+// C_pp is stored as two row groups (rows 0-2, rows 3-5) of 18 elements, ONE PADDING ELEMENT APART: in the Riccati step
+// lanes c = 0 and c = 1 of every quad read the same position of their own row group at once, and with tiles of 8
+// problems per element an even element distance would put both groups on the same 16 shared-memory banks
+// (ncu: 2-3 excess wavefronts on each of those 18 loads); an odd distance puts them on the two halves.
+constexpr int R_CPP_GROUP = 19;
+constexpr int R_CPV = 101, R_CVP = 137;  // only in records of a Q with pose/velocity coupling (173 doubles)
+constexpr int REC = 101;  // elements 0..100 of a record in the fused kernel's shared memory (= 5 mod 16)
 constexpr int X_M = 0, X_K = 148, X_VX = 196, X_Q = 208, XCH = 224;
 __host__ __device__ constexpr int stride(int kpp) {
   const int base = kpp * REC + XCH;
@@ -80,7 +85,7 @@ QD void m3_madd_hat(const double *M, const double *w, double *C) {
 struct G4Layout {
   __host__ __device__ static constexpr int cx(int j) { return R_CX + j; }
   __host__ __device__ static constexpr int cu(int j) { return R_CU + j; }
-  __host__ __device__ static constexpr int cpp(int i, int j) { return R_CPP + 6 * i + j; }
+  __host__ __device__ static constexpr int cpp(int i, int j) { return R_CPP + 6 * i + j + (i >= 3 ? R_CPP_GROUP - 18 : 0); }
   __host__ __device__ static constexpr int cpv(int i, int j) { return R_CPV + 6 * i + j; }
   __host__ __device__ static constexpr int cvp(int i, int j) { return R_CVP + 6 * i + j; }
 };

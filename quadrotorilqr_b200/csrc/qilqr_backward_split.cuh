@@ -24,9 +24,10 @@
 namespace qilqr {
 namespace g4 {
 
-// record elements per knot: 100 for Q = blkdiag(Q_pp, Q_vv), 172 for a Q with pose/velocity coupling
-__host__ __device__ constexpr int rect(bool denseq) { return denseq ? 172 : 100; }
-// doubles per (tile of 8 problems, knot): 6400 B / 11008 B, multiples of 16
+// record elements per knot: 101 for Q = blkdiag(Q_pp, Q_vv) (100 values + 1 padding element, see R_CPP_GROUP), 173 for
+// a Q with pose/velocity coupling
+__host__ __device__ constexpr int rect(bool denseq) { return denseq ? 173 : 101; }
+// doubles per (tile of 8 problems, knot): 6464 B / 11072 B, multiples of 16
 __host__ __device__ constexpr int tile_doubles(bool denseq) { return rect(denseq) * 8; }
 constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
 __host__ __device__ constexpr int split_smem_doubles(bool denseq) { return 2 * tile_doubles(denseq) + 8 * XS + 36 + 2; }

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) k_riccati_g16(const __grid_constant__ Dev
 #pragma unroll
         for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
-          for (int cj = 0; cj < 3; ++cj) Qb[3 * ri + cj] = rec[(R_CPP + 6 * (3 * r + ri) + 3 * c + cj) * RS];
+          for (int cj = 0; cj < 3; ++cj) Qb[3 * ri + cj] = rec[(R_CPP + R_CPP_GROUP * r + 6 * ri + 3 * c + cj) * RS];
       } else if (r >= 2 && c >= 2) {
 #pragma unroll
         for (int ri = 0; ri < 3; ++ri)

@@ -133,7 +133,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     // C_pv and C_vp vanish (and are not stored) when Q has no pose/velocity coupling (!DENSEQ).
     const bool lo = c < 2;
     if (DENSEQ) {
-      const double *srcA = lo ? (rec + (R_CPP + 18 * c) * RS) : (rec + (R_CVP + 18 * (c - 2)) * RS);
+      const double *srcA = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (rec + (R_CVP + 18 * (c - 2)) * RS);
       const double *srcB = lo ? (rec + (R_CPV + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
       const int sB = lo ? RS : 1;  // the record is strided, the 2*Q_vv table is dense
 #pragma unroll
@@ -146,7 +146,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
           Q3[3 * ri + cj] = srcB[(6 * ri + 3 + cj) * sB];
         }
     } else {
-      const double *src = lo ? (rec + (R_CPP + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
+      const double *src = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (s2Qvv + 18 * (c - 2));
       const int sst = lo ? RS : 1;
 #pragma unroll
       for (int ri = 0; ri < 3; ++ri)
