@@ -408,7 +408,8 @@ def main():
 
     STAT_KEYS = ("backward_ms", "rollout_ms", "backward_problem_knots", "rollout_problem_knots",
                  "problem_iterations", "problem_rollouts", "solver_iterations", "bulk_wall_ms", "tail_wall_ms",
-                 "backward_ms_bulk", "rollout_ms_bulk", "backward_problem_knots_bulk", "kernel_launches")
+                 "backward_ms_bulk", "rollout_ms_bulk", "backward_problem_knots_bulk", "backward_launches_bulk",
+                 "kernel_launches")
 
     def device_begin(j, h):
         with torch.cuda.stream(streams[j][h]):
@@ -650,7 +651,7 @@ def main():
     achieved_all = tflops(bwd_knots, f_bwd, bwd_ms)                # every launch, the latency-bound tail included
     exe = counters["executed_flops_per_problem_knot"] if counters else None
     executed = tflops(bwd_knots_bulk, exe, bwd_ms_bulk) if exe else None
-    n_bulk_steps = n_serial
+    n_bulk_launches = max(1, ser["backward_launches_bulk"])  # backward passes (launch pairs) timed as "bulk"
     roofline = {
         "kernel": ("backward pass = k_linearise + k_riccati_g4 (ILQR::backwards_pass, ilqr.hh:97-147)"
                    if not args.model_variant else
@@ -671,12 +672,15 @@ def main():
         "peak_source": "measured in this run: register-resident DFMA kernel (qilqr_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "flops_per_problem_knot": f_bwd,
-        "traffic": (counters["dram_bytes_per_problem_knot"] * bwd_knots_bulk / max(1, n_bulk_steps)) if counters else None,
-        "traffic_note": ("dram__bytes_read+write per problem-knot from the committed ncu capture x the problem-knots of "
-                         "one step's bulk launches; algorithmic: "
+        "traffic": (counters["dram_bytes_per_problem_knot"] * bwd_knots_bulk / n_bulk_launches) if counters else None,
+        "traffic_note": ("per backward pass (k_linearise + k_riccati_g4 launch pair), averaged over the bulk launches: "
+                         "dram__bytes_read+write per problem-knot from the committed ncu capture x the mean problem-knots "
+                         "of a bulk launch; algorithmic: "
                          f"{counters['algorithmic_bytes_per_problem_knot']:.0f} B per problem-knot -- the difference is the "
                          "linearisation record written by k_linearise and read once by k_riccati_g4") if counters else None,
-        "algorithmic_bytes": 552.0 * bwd_knots_bulk / max(1, n_bulk_steps),
+        "algorithmic_bytes": 552.0 * bwd_knots_bulk / n_bulk_launches,
+        "bulk_backward_passes_per_step": n_bulk_launches / n_serial,
+        "mean_bulk_launch_ms": bwd_ms_bulk / n_bulk_launches,
         "timed": (f"CUDA events on the solver's stream around every launch of {n_serial} un-pipelined steps run right "
                   "after the timed region (kernels of different handles overlap inside it)"),
         "bulk_ms_per_step": bwd_ms_bulk / n_serial, "all_launches_ms_per_step": bwd_ms / n_serial,

@@ -329,6 +329,7 @@ typedef struct {
   double backward_ms_bulk;
   double rollout_ms_bulk;
   int64_t backward_problem_knots_bulk;
+  int64_t backward_launches_bulk; /* backward passes (linearisation + Riccati launch pairs) issued in the bulk */
 } qilqr_solve_stats_t;
 int qilqr_last_solve_stats(const qilqr_solver_t *solver, qilqr_solve_stats_t *out);
 /* Enable/disable per-kernel CUDA-event timing (adds a few microseconds per launch). */

@@ -80,6 +80,7 @@ class SolveStats(C.Structure):
         ("backward_ms_bulk", C.c_double),
         ("rollout_ms_bulk", C.c_double),
         ("backward_problem_knots_bulk", C.c_int64),
+        ("backward_launches_bulk", C.c_int64),
     ]
 
 

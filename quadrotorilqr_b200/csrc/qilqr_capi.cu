@@ -584,7 +584,10 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
         if ((rc = launch_backward(S, ba))) return rc;
       }
       S->stats.backward_problem_knots += int64_t(n_active) * N;
-      if (!S->in_tail) S->stats.backward_problem_knots_bulk += int64_t(n_active) * N;
+      if (!S->in_tail) {
+        S->stats.backward_problem_knots_bulk += int64_t(n_active) * N;
+        ++S->stats.backward_launches_bulk;
+      }
       ++S->launches;
     }
     if (P_alpha > 1 && epoch > 0 && (S->wide_first || n_alive > n_active)) {  // someone is backtracking
@@ -1059,6 +1062,7 @@ int qilqr_mpc_run_device(qilqr_solver_t *S, int steps, int B, int N, const doubl
     total_stats.backward_ms_bulk += S->stats.backward_ms_bulk;
     total_stats.rollout_ms_bulk += S->stats.rollout_ms_bulk;
     total_stats.backward_problem_knots_bulk += S->stats.backward_problem_knots_bulk;
+    total_stats.backward_launches_bulk += S->stats.backward_launches_bulk;
     total_stats.bulk_wall_ms += S->stats.bulk_wall_ms;
     total_stats.tail_wall_ms += S->stats.tail_wall_ms;
     double *u_log = d_control_log ? d_control_log + size_t(t) * 4 * B : nullptr;
