@@ -465,6 +465,8 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
     QCUDA(S, S->hist_d.ensure(sizeof(double) * size_t(hist_cap) * B));
     d_hist = S->hist_d.as<double>();
     S->last_hist_internal = true;
+    // entries a problem never reaches read back as zero
+    QCUDA(S, cudaMemsetAsync(d_hist, 0, sizeof(double) * size_t(hist_cap) * B, S->stream));
   }
   if (d_hist == S->hist_d.as<double>()) S->last_hist_internal = true;  // (the host path's own staging buffer)
   S->last_hist_cap = d_hist ? hist_cap : 0;

@@ -38,3 +38,15 @@ if __name__ == "__main__":
     print(run(base, 70, 7)["rollouts"])                                               # role-specialised rollout (3 CTAs, ragged)
     print(run(dataclasses.replace(base, symmetrize_vxx=True), 11, 6, model_flags=3)["backward_passes"])  # dense kernels, RK4 + Coriolis
     print(run(base, 9, 5, model_flags=4)["backward_passes"])                          # dense kernels, reference model
+    # round 2: the 16-lane Riccati kernel is what the small cases above use; force the 4-lane one as well, the
+    # persistent tail kernel, tail compaction at a small threshold, sampled debug rings, controls-in entry point
+    print(run(base, 21, 9, {"QILQR_G16_THRESHOLD": "0"})["backward_passes"])
+    print(run(base, 37, 8, {"QILQR_PERSISTENT_TAIL": "1", "QILQR_PERSIST_THRESHOLD": "12", "QILQR_HI_THRESHOLD": "20"})["backward_passes"])
+    m = problems.hover_model()
+    s = BatchILQR(m["mass_kg"], m["inertia"], m["arm_length_m"], m["torque_to_thrust_ratio_m"], m["g_mpss"], m["Q"], m["R"],
+                  m["dt_s"], dataclasses.replace(base, populate_debug=True))
+    d = problems.hover_desired_trajectory(7)
+    x0 = problems.hover_initial_states(19, seed=4)
+    s.set_debug_sampling(np.array([3, 17, 0], dtype=np.int32), every=2, ring=2)
+    r = s.solve_from_controls(x0, np.tile(d[0, 14:18], (7, 1)), d, want_controls=True)
+    print(r["results"]["backward_passes"], s.read_debug_samples(7)["counts"], s.last_cost_history(count=19).shape)
