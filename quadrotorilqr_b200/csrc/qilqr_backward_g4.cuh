@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(32) k_backward_g4(const __grid_constant__ Devi
     for (int j = 0; j < KPP; ++j) {
       const int ii = i - j;
       if (ii < 0) break;
-      riccati_step<1>(p, a, recs + j * REC, s2Qvv, xch, c, valid, ii, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
+      riccati_step<1>(p, a, recs + j * REC, s2Qvv, xch, c, a.pr.gk + size_t(c) * B + b, a.pr.gK + size_t(3 * c) * B + b, ii, B,
+                      V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
     }
   }
 

@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
 #pragma unroll
   for (int e = 0; e < 12; ++e) vx[e] = 0.0;
   double QuTk = 0.0, kTQuuk = 0.0;
+  // (padding quads shadow the last problem: they rewrite its gains with identical values)
+  double *gk_lane = a.pr.gk + size_t(c) * B + b, *gK_lane = a.pr.gK + size_t(3 * c) * B + b;
 
 #pragma unroll 1
   for (int i = N - 1; i >= 0; --i) {
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
     }
     if (s == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
     else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-    riccati_step<8, DENSEQ>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, valid, i, B, b, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
+    riccati_step<8, DENSEQ>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, gk_lane, gK_lane, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
   }
 
   if (!valid || c != 0) return;

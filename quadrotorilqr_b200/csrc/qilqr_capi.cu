@@ -118,7 +118,7 @@ struct qilqr_solver {
   DeviceBuffer buf1, gk, gK, state_d, state_i, lists, desired_soa, traj_soa, stage_a, stage_b, stage_c, results_d,
       hist_d, debug_d, misc, wide_d, rec_d, totals_d, stage_d;
   // dense mini-batch for the tail of a solve (k_tail_gather / k_tail_scatter)
-  DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map, tail_lists, rec_tail_d;
+  DeviceBuffer tail_traj, tail_gains, tail_des, tail_sd, tail_si, tail_hist, tail_map, tail_lists, rec_tail_d, tail_scratch;
   bool tail_compaction = true;  // QILQR_TAIL_COMPACTION=0 keeps the stragglers in the big batch's layout
   bool persistent_tail = false;  // QILQR_PERSISTENT_TAIL=1: one kernel finishes the solve on the device once at most
   int persist_threshold = 64;    // `persist_threshold` problems are alive (frees the host thread: begin / finish API)
@@ -573,8 +573,11 @@ int solve_core(qilqr_solver *S, int B, int N, const double *d_desired, int Bd, d
       if (S->rec_tail_d.ensure(sizeof(double) * size_t(tiles) * 8 * N * g4::rect(dq)) != cudaSuccess)
         return fail(S, QILQR_ERR_OUT_OF_MEMORY, "out of device memory for the linearisation records");
       const size_t smem = sizeof(double) * tp::smem_doubles(dq);
-      if (dq) k_tail_persistent<true><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), alive, n_alive, epoch);
-      else k_tail_persistent<false><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), alive, n_alive, epoch);
+      if (S->tail_scratch.ensure(sizeof(double) * size_t(N) * 52 * size_t(pr.B)) != cudaSuccess)
+        return fail(S, QILQR_ERR_OUT_OF_MEMORY, "out of device memory for the tail kernel's scratch gains");
+      double *scr = S->tail_scratch.as<double>();
+      if (dq) k_tail_persistent<true><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), scr, alive, n_alive, epoch);
+      else k_tail_persistent<false><<<tiles, 96, smem, st_>>>(S->p, pr, st, S->rec_tail_d.as<double>(), scr, alive, n_alive, epoch);
       ++S->launches;
       persistent_launched = true;
       break;
@@ -831,7 +834,7 @@ void qilqr_destroy(qilqr_solver_t *S) {
                           &S->traj_soa, &S->stage_a, &S->stage_b, &S->stage_c, &S->results_d, &S->hist_d,
                           &S->debug_d, &S->misc, &S->wide_d, &S->rec_d, &S->totals_d, &S->tail_traj, &S->tail_gains,
                           &S->tail_des, &S->tail_sd, &S->tail_si, &S->tail_hist, &S->tail_map, &S->tail_lists,
-                          &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count, &S->stage_d})
+                          &S->rec_tail_d, &S->dbg_sample, &S->dbg_traj, &S->dbg_iters, &S->dbg_costs, &S->dbg_count, &S->stage_d, &S->tail_scratch})
     b->release();
   for (auto e : S->event_pool) cudaEventDestroy(e);
   if (S->user_lib) cudaLibraryUnload(S->user_lib);

@@ -53,6 +53,17 @@
 
 namespace qilqr {
 
+// Branch-free selection (the compiler turns chained `c == k ? ... : ...` on doubles into branches otherwise).
+QD double selp(double a, double b, bool take_a) {
+  double r;
+  asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"(int(take_a)));
+  return r;
+}
+// v[c] for c in 0..3
+QD double sel4(int c, double v0, double v1, double v2, double v3) {
+  return selp(selp(v3, v2, (c & 1) != 0), selp(v1, v0, (c & 1) != 0), (c & 2) != 0);
+}
+
 constexpr double kEps = 1e-14;  // manif Constants<double>::eps
 
 // Solver constants, passed to every kernel by value (constant bank, so matrix

@@ -4,8 +4,9 @@
 // memory, stride RS = 1) and the split kernel (k_riccati_g4: record tiles [elem][8 problems]
 // brought in by TMA bulk copies, stride RS = 8).  See qilqr_backward_g4.cuh for the algorithm.
 //   rec    : this knot's linearisation record, element e at rec[e * RS]
-//   valid  : write this problem's gains (false for the padding quads of the last tile, and for quads of the
-//            persistent tail kernel whose problem is not in its backward pass)
+//   gk_lane, gK_lane : where this lane's gains go -- gk + c * B + b and gK + 3 c * B + b of the problem (the padding
+//            quads of a last tile shadow the last problem and rewrite identical values; quads of the persistent
+//            tail kernel whose problem is not in its backward pass get a scratch array)
 //   s2Qvv  : 2*Q_vv (6x6), dense
 //   xch    : this problem's exchange area (g4::XCH doubles)
 //   V0..V3 : the lane's column block c of V_xx (in/out);  vx: v_x (replicated, in/out)
@@ -24,7 +25,7 @@ QD void ld9s(const double *s, double *r) {
 
 template <int RS, bool DENSEQ = false>
 QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double *rec, const double *s2Qvv,
-                     double *xch, const int c, const bool valid, const int ii, const int B, const int b, double *V0,
+                     double *xch, const int c, double *gk_lane, double *gK_lane, const int ii, const int B, double *V0,
                      double *V1, double *V2, double *V3, double *vx, double *V88, double &QuTk, double &kTQuuk) {
   const double dgz[3] = {rec[R_GZ * RS], rec[(R_GZ + 1) * RS], rec[(R_GZ + 2) * RS]};
   const double ndgz[3] = {-dgz[0], -dgz[1], -dgz[2]};
@@ -223,20 +224,19 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
       double acc = KQ[4 * s] * k[0];
 #pragma unroll
       for (int l = 1; l < 4; ++l) acc = QFMA(KQ[4 * s + l], k[l], acc);
-      const double qx = (c == 0) ? Qx[s] : (c == 1) ? Qx[3 + s] : (c == 2) ? Qx[6 + s] : Qx[9 + s];
+      const double qx = sel4(c, Qx[s], Qx[3 + s], Qx[6 + s], Qx[9 + s]);
       xch[X_VX + 3 * c + s] = qx - acc;
     }
+    // rows 12 jj + 3 c + s of K and row c of k at this knot: one 64-bit base per knot, 32-bit row offsets
+    double *gKk = gK_lane + size_t(ii) * 48 * size_t(B);
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         xch[X_K + 12 * jj + 3 * c + s] = Ks[3 * jj + s];
-        if (valid) a.pr.gK[row_index(ii, 12 * jj + 3 * c + s, 48, B, b)] = Ks[3 * jj + s];
+        gKk[(12 * jj + s) * B] = Ks[3 * jj + s];
       }
-    if (valid) {
-      const double kc = (c == 0) ? k[0] : (c == 1) ? k[1] : (c == 2) ? k[2] : k[3];
-      a.pr.gk[row_index(ii, c, 4, B, b)] = kc;
-    }
+    gk_lane[size_t(ii) * 4 * size_t(B)] = sel4(c, k[0], k[1], k[2], k[3]);
   }
   __syncwarp();
 

@@ -35,8 +35,8 @@ __host__ __device__ constexpr int smem_doubles(bool denseq) {
 
 template <bool DENSEQ>
 __global__ void __launch_bounds__(96, 1) k_tail_persistent(const __grid_constant__ DeviceParams p, const Problem pr,
-                                                           const SolveState st, double *rec_g, const int *list,
-                                                           const int n, const int epoch) {
+                                                           const SolveState st, double *rec_g, double *scratch_gains,
+                                                           const int *list, const int n, const int epoch) {
   using namespace g4;
   constexpr int TILE = tile_doubles(DENSEQ);
   extern __shared__ __align__(128) double smem[];
@@ -113,8 +113,11 @@ __global__ void __launch_bounds__(96, 1) k_tail_persistent(const __grid_constant
       for (int i = N - 1; i >= 0; --i) {
         const int s = (N - 1 - i) & 1;
         if (warp == 0) {
-          riccati_step<8, DENSEQ>(p, ba, bufs + s * TILE + q, s2Qvv, xch_all + q * XS, c, act, i, B, t, V0, V1, V2, V3,
-                                  vx, V88, QuTk, kTQuuk);
+          // (quads whose problem is not in its backward pass sweep stale records: their gains go to a scratch array
+          //  laid out like the real one)
+          double *gk0 = act ? pr.gk : scratch_gains, *gK0 = act ? pr.gK : scratch_gains + size_t(N) * 4 * B;
+          riccati_step<8, DENSEQ>(p, ba, bufs + s * TILE + q, s2Qvv, xch_all + q * XS, c, gk0 + size_t(c) * B + t,
+                                  gK0 + size_t(3 * c) * B + t, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
         } else if (i > 0) {
           for (int e = tid - 32; e < TILE; e += 64) bufs[(s ^ 1) * TILE + e] = rec_tile[size_t(i - 1) * TILE + e];
         }
