@@ -780,6 +780,11 @@ int qilqr_create(const qilqr_model_t *model, const double *Q, const double *R, d
   for (int i = 0; i < 16; ++i) p.Bu[i] = dt_s * p.JuC[i];
   for (int i = 0; i < 144; ++i) p.Q[i] = Q[i];
   for (int i = 0; i < 16; ++i) p.R[i] = R[i];
+  p.q_diagonal = 1;
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 12; ++j)
+      if (i != j && Q[12 * i + j] != 0.0) p.q_diagonal = 0;
+  if (const char *e = std::getenv("QILQR_Q_DIAGONAL")) p.q_diagonal = p.q_diagonal && std::atoi(e) != 0;
   S->p = p;
   for (int i = 0; i < 6; ++i)
     for (int j = 6; j < 12; ++j)

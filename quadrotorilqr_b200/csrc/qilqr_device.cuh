@@ -84,6 +84,7 @@ struct DeviceParams {
   // model variant behind the ModelT concept (qilqr_model_generic.cuh); 0/0 = the reference's QuadrotorModel
   int integrator;  // 0: explicit Euler (quadrotor_model.cc:33-49), 1: RK4 (the scheme commented out at :51-63)
   int coriolis;    // 1: adds -omega x v to the body linear acceleration
+  int q_diagonal;  // Q has no off-diagonal entry: the cost skips the products with structural zeros
 };
 
 // ---------------------------------------------------------------------------
@@ -497,6 +498,16 @@ QD void state_minus(const double *x /*13*/, const double *xd /*13*/, double *dx 
 // cost = dx^T Q dx + du^T R du, evaluated as (dx^T Q) dx   (cost.hh:47-48)
 QD double quadratic_cost_state(const DeviceParams &p, const double *dx) {
   double cx = 0.0;
+  if (p.q_diagonal) {
+    // dx^T Q with a diagonal Q: every other term of the dense chain below is (+-0) + (+-0), so column j of the
+    // product is the rounded dx_j * Q_jj either way; the sum over j keeps its order
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const double y = dx[j] * p.Q[13 * j];
+      cx = (j == 0) ? y * dx[0] : QFMA(y, dx[j], cx);
+    }
+    return cx;
+  }
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
     double y = dx[0] * p.Q[j];

@@ -241,6 +241,14 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
     for (int c = 0; c < 4; ++c) ubar[c] = ldg_early(&cur[row_index(i, 13 + c, 17, B, b)]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) gk[e] = ldg_early(&a.pr.gk[row_index(i, e, 4, B, b)]);
+    // the state part of the cost needs nothing that was just requested: it runs while the loads are in flight
+    double cx = 0.0, ud[4] = {0.0, 0.0, 0.0, 0.0};
+    if (want_cost) {
+      double xd[13], dx[12];
+      load_point(a.pr.desired, i, Bd, bd, xd, ud);
+      state_minus(x, xd, dx, nullptr);
+      cx = quadratic_cost_state(p, dx);
+    }
 #pragma unroll
     for (int e = 0; e < 48; ++e) gK[e] = ldg_early(&a.pr.gK[row_index(i, e, 48, B, b)]);
     double d[12];
@@ -255,12 +263,10 @@ __global__ void __launch_bounds__(128, QILQR_ROLLOUT_MINB) k_rollout(const __gri
     }
     if (cand) store_point(cand, i, B, b, x, u);
     if (want_cost) {
-      double xd[13], ud[4], dx[12], du[4];
-      load_point(a.pr.desired, i, Bd, bd, xd, ud);
-      state_minus(x, xd, dx, nullptr);
+      double du[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) du[j] = u[j] - ud[j];
-      cost = cost + quadratic_cost(p, dx, du);
+      cost = cost + (cx + quadratic_cost_control(p, du));
     }
     // also after the last knot, as ilqr.hh:168 does; result unused
     if (GENERIC) gm::discrete_step_any(p, x, u);
