@@ -682,14 +682,14 @@ int solve_finish(qilqr_solver *S, SolveCtx &cx) {
 }
 
 int pack_traj(qilqr_solver *S, int B, int N, const double *d_aos, double *d_soa) {
-  dim3 grid(blocks_for(B, 32), unsigned(N < 64 ? N : 64));
-  k_pack<<<grid, 576, 0, S->stream>>>(d_aos, d_soa, B, N);
+  dim3 grid(blocks_for(B, 32), unsigned(std::min((N + PACK_K - 1) / PACK_K, 16)));
+  k_pack<<<grid, PACK_THREADS, 0, S->stream>>>(d_aos, d_soa, B, N);
   ++S->launches;
   return QILQR_OK;
 }
 int unpack_traj(qilqr_solver *S, int B, int N, const double *d_soa, double *d_aos) {
-  dim3 grid(blocks_for(B, 32), unsigned(N < 64 ? N : 64));
-  k_unpack<<<grid, 576, 0, S->stream>>>(d_soa, d_aos, B, N);
+  dim3 grid(blocks_for(B, 32), unsigned(std::min((N + PACK_K - 1) / PACK_K, 16)));
+  k_unpack<<<grid, PACK_THREADS, 0, S->stream>>>(d_soa, d_aos, B, N);
   ++S->launches;
   return QILQR_OK;
 }

@@ -1208,37 +1208,43 @@ __global__ void k_debug_ring_capture(Problem pr, SolveState st, DebugRing dr, in
 
 // ---------------------------------------------------------------------------
 // AoS [B][N][18] <-> SoA [N][17][B] transposition through shared memory.
-// Block: 32 problems x 18 components; grid.x = ceil(B/32), grid.y strides over knots.
+// Block: 32 problems x PACK_K consecutive knots (PACK_K * 18 contiguous doubles per problem on the AoS side, 32
+// contiguous problems per row on the SoA side); grid.x = ceil(B/32), grid.y strides over groups of knots.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(576) k_pack(const double *aos, double *soa, int B, int N) {
-  __shared__ double tile[18][33];
+constexpr int PACK_K = 4, PACK_W = PACK_K * 18, PACK_THREADS = 256;
+__global__ void __launch_bounds__(PACK_THREADS) k_pack(const double *aos, double *soa, int B, int N) {
+  __shared__ double tile[32][PACK_W + 1];
   const int b0 = blockIdx.x * 32, tid = threadIdx.x;
-  for (int i = blockIdx.y; i < N; i += gridDim.y) {
-    {
-      const int c = tid % 18, bl = tid / 18;
-      if (b0 + bl < B) tile[c][bl] = aos[(size_t(b0 + bl) * N + i) * 18 + c];
+  for (int i0 = blockIdx.y * PACK_K; i0 < N; i0 += gridDim.y * PACK_K) {
+    const int w = min(PACK_K, N - i0) * 18;
+    for (int e = tid; e < 32 * PACK_W; e += PACK_THREADS) {
+      const int bl = e / PACK_W, col = e % PACK_W;
+      if (col < w && b0 + bl < B) tile[bl][col] = aos[(size_t(b0 + bl) * N + i0) * 18 + col];
     }
     __syncthreads();
-    {
-      const int bl = tid % 32, c = tid / 32;
-      if (c >= 1 && b0 + bl < B) soa[(size_t(i) * 17 + (c - 1)) * B + b0 + bl] = tile[c][bl];
+    for (int e = tid; e < 32 * PACK_W; e += PACK_THREADS) {
+      const int bl = e % 32, col = e / 32, c = col % 18;
+      if (c >= 1 && col < w && b0 + bl < B)
+        soa[(size_t(i0 + col / 18) * 17 + (c - 1)) * B + b0 + bl] = tile[bl][col];
     }
     __syncthreads();
   }
 }
 // Leaves column 0 (time_s) of the AoS buffer untouched.
-__global__ void __launch_bounds__(576) k_unpack(const double *soa, double *aos, int B, int N) {
-  __shared__ double tile[18][33];
+__global__ void __launch_bounds__(PACK_THREADS) k_unpack(const double *soa, double *aos, int B, int N) {
+  __shared__ double tile[32][PACK_W + 1];
   const int b0 = blockIdx.x * 32, tid = threadIdx.x;
-  for (int i = blockIdx.y; i < N; i += gridDim.y) {
-    {
-      const int bl = tid % 32, c = tid / 32;
-      if (c >= 1 && b0 + bl < B) tile[c][bl] = soa[(size_t(i) * 17 + (c - 1)) * B + b0 + bl];
+  for (int i0 = blockIdx.y * PACK_K; i0 < N; i0 += gridDim.y * PACK_K) {
+    const int w = min(PACK_K, N - i0) * 18;
+    for (int e = tid; e < 32 * PACK_W; e += PACK_THREADS) {
+      const int bl = e % 32, col = e / 32, c = col % 18;
+      if (c >= 1 && col < w && b0 + bl < B)
+        tile[bl][col] = soa[(size_t(i0 + col / 18) * 17 + (c - 1)) * B + b0 + bl];
     }
     __syncthreads();
-    {
-      const int c = tid % 18, bl = tid / 18;
-      if (c >= 1 && b0 + bl < B) aos[(size_t(b0 + bl) * N + i) * 18 + c] = tile[c][bl];
+    for (int e = tid; e < 32 * PACK_W; e += PACK_THREADS) {
+      const int bl = e / PACK_W, col = e % PACK_W;
+      if (col % 18 >= 1 && col < w && b0 + bl < B) aos[(size_t(b0 + bl) * N + i0) * 18 + col] = tile[bl][col];
     }
     __syncthreads();
   }

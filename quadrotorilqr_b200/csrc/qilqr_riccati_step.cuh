@@ -147,25 +147,32 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
           Q3[3 * ri + cj] = srcB[(6 * ri + 3 + cj) * sB];
         }
     } else {
+      // Lanes 0, 1 own pose rows [C_pp | 0], lanes 2, 3 velocity rows [0 | 2 Q_vv]: one 3x6 source per lane, and the
+      // zero half enters as source * 0.0 inside the fused add below instead of a select per element.
       const double *src = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (s2Qvv + 18 * (c - 2));
       const int sst = lo ? RS : 1;
 #pragma unroll
       for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
         for (int cj = 0; cj < 3; ++cj) {
-          const double a0 = src[(6 * ri + cj) * sst], a1 = src[(6 * ri + 3 + cj) * sst];
-          Q0[3 * ri + cj] = lo ? a0 : 0.0;
-          Q1[3 * ri + cj] = lo ? a1 : 0.0;
-          Q2[3 * ri + cj] = lo ? 0.0 : a0;
-          Q3[3 * ri + cj] = lo ? 0.0 : a1;
+          Q0[3 * ri + cj] = src[(6 * ri + cj) * sst];
+          Q1[3 * ri + cj] = src[(6 * ri + 3 + cj) * sst];
         }
     }
+    // C_xx[r,:] + (A^T V A)[r,:].  cadd(C, m, T) = C * m + T with m = 1 (exact: C + T) or 0 (T, up to the sign of a
+    // zero T); DENSEQ adds the stored blocks directly.
+    const double mlo = lo ? 1.0 : 0.0, mhi = lo ? 0.0 : 1.0;
     double X0[9], X1[9], X2[9], X3[9], Ab[9], T[9];
     ld9(xch + moff(c, 0), X0);
     ld9s<RS>(rec + R_RE * RS, Ab);
     m3_mul(X0, Ab, T);
+    double C0[9], C1[9];  // the lane's 3x6 source (!DENSEQ)
 #pragma unroll
-    for (int e = 0; e < 9; ++e) Q0[e] += T[e];
+    for (int e = 0; e < 9; ++e) {
+      C0[e] = Q0[e];
+      C1[e] = Q1[e];
+      Q0[e] = DENSEQ ? Q0[e] + T[e] : QFMA(C0[e], mlo, T[e]);
+    }
     double Tb[9];
     ld9s<RS>(rec + R_TE * RS, Tb);
     m3_mul(X0, Tb, T);
@@ -174,11 +181,11 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     ld9(xch + moff(c, 2), X2);
     m3_madd_hat(X2, dgz, T);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) Q1[e] += T[e];
+    for (int e = 0; e < 9; ++e) Q1[e] = DENSEQ ? Q1[e] + T[e] : QFMA(C1[e], mlo, T[e]);
     ld9s<RS>(rec + R_DJR * RS, Ab);
     m3_mul(X0, Ab, T);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) Q2[e] += T[e] + X2[e];
+    for (int e = 0; e < 9; ++e) Q2[e] = DENSEQ ? Q2[e] + (T[e] + X2[e]) : QFMA(C0[e], mhi, T[e] + X2[e]);
     ld9s<RS>(rec + R_DQB * RS, Tb);
     m3_mul(X0, Tb, T);
     m3_madd(X1, Ab, T);
@@ -186,7 +193,7 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     ld9s<RS>(rec + R_WD * RS, Tb);
     m3_madd(X3, Tb, T);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) Q3[e] += T[e];
+    for (int e = 0; e < 9; ++e) Q3[e] = DENSEQ ? Q3[e] + T[e] : QFMA(C1[e], mhi, T[e]);
     // Q.xu[r] = M[r, 8] B[8,:] + M[r, 9:12] B[9:12,:]
 #pragma unroll
     for (int s = 0; s < 3; ++s)
