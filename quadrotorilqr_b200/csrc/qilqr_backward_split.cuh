@@ -30,7 +30,7 @@ __host__ __device__ constexpr int rect(bool denseq) { return denseq ? 173 : 101;
 // doubles per (tile of 8 problems, knot): 6464 B / 11072 B, multiples of 16
 __host__ __device__ constexpr int tile_doubles(bool denseq) { return rect(denseq) * 8; }
 constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
-__host__ __device__ constexpr int split_smem_doubles(bool denseq) { return 2 * tile_doubles(denseq) + 8 * XS + 36 + 2; }
+__host__ __device__ constexpr int split_smem_doubles(bool denseq) { return tile_doubles(denseq) + 8 * XS + 36 + 2; }
 
 QD uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 QD void mbar_init(uint64_t *bar, int count) {
@@ -84,9 +84,34 @@ __global__ void __launch_bounds__(128) k_linearise(const __grid_constant__ Devic
   linearise_to_record<8, DENSEQ>(p, x, u, xd, ud, dst);
 }
 
+namespace g4 {
+// riccati_step's record_done hook of the kernel below: lane 0 starts the bulk copy of the next knot's record tile into
+// the (single) record buffer.  fence.proxy.async orders the warp's generic-proxy reads of the buffer, which the
+// __syncwarp before the hook has collected, before the async-proxy write.
+struct NextRecord {
+  static constexpr bool kActive = true;
+  double *bufs;
+  const double *next;
+  uint64_t *mbar;
+  int lane;
+  uint32_t bytes;
+  QD void operator()() const {
+    if (next && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(mbar, bytes);
+      bulk_copy_g2s(bufs, next, bytes, mbar);
+    }
+  }
+};
+}  // namespace g4
+// One warp per tile of 8 problems, 4 lanes per problem.  ONE record buffer: the TMA bulk copy of knot i-1 is issued
+// as soon as the warp has made its last read of record i (after step 3 of the Riccati step) and lands during steps
+// 4-6, which do not touch the record.  (A second buffer with the copy issued at the top of the knot measured 2 %
+// slower, and 9 or 10 resident warps per SM at 224 / 200 registers -- which the smaller footprint would allow -- no
+// faster: profiles/README.md.)
 template <bool DENSEQ>
 __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ DeviceParams p,
-                                                   const __grid_constant__ BackwardArgs a, const double *rec_g) {
+                                                                       const __grid_constant__ BackwardArgs a, const double *rec_g) {
   using namespace g4;
   constexpr int TILE = tile_doubles(DENSEQ);
   extern __shared__ __align__(128) double smem[];
@@ -98,13 +123,12 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
   const int b = a.list ? a.list[tt] : tt;
   const int B = a.pr.B, N = a.pr.N;
   double *bufs = smem;
-  double *xch = smem + 2 * TILE + q * XS;
-  double *s2Qvv = smem + 2 * TILE + 8 * XS;
+  double *xch = smem + TILE + q * XS;
+  double *s2Qvv = smem + TILE + 8 * XS;
   uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36);
   for (int e = lane; e < 36; e += 32) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -114,8 +138,7 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
     mbar_expect_tx(&mbar[0], kBytes);
     bulk_copy_g2s(bufs, src + size_t(N - 1) * TILE, kBytes, &mbar[0]);
   }
-  uint32_t phase0 = 0, phase1 = 0;
-
+  uint32_t phase0 = 0;
   double V0[9], V1[9], V2[9], V3[9], vx[12], V88[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) V88[e] = 0.0;
@@ -124,24 +147,14 @@ __global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ Devic
 #pragma unroll
   for (int e = 0; e < 12; ++e) vx[e] = 0.0;
   double QuTk = 0.0, kTQuuk = 0.0;
-  // (padding quads shadow the last problem: they rewrite its gains with identical values)
   double *gk_lane = a.pr.gk + size_t(c) * B + b, *gK_lane = a.pr.gK + size_t(3 * c) * B + b;
-
 #pragma unroll 1
   for (int i = N - 1; i >= 0; --i) {
-    const int s = (N - 1 - i) & 1;
-    if (i > 0 && lane == 0) {
-      // the other buffer was last read (generic proxy) during the previous knot's step, which every
-      // lane has left through the step's final __syncwarp: order those reads before the async write
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[s ^ 1], kBytes);
-      bulk_copy_g2s(bufs + (s ^ 1) * TILE, src + size_t(i - 1) * TILE, kBytes, &mbar[s ^ 1]);
-    }
-    if (s == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
-    else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-    riccati_step<8, DENSEQ>(p, a, bufs + s * TILE + q, s2Qvv, xch, c, gk_lane, gK_lane, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
+    mbar_wait(&mbar[0], phase0);
+    phase0 ^= 1;
+    g4::NextRecord hook{bufs, i > 0 ? src + size_t(i - 1) * TILE : nullptr, &mbar[0], lane, kBytes};
+    riccati_step<8, DENSEQ, g4::NextRecord>(p, a, bufs + q, s2Qvv, xch, c, gk_lane, gK_lane, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk, hook);
   }
-
   if (!valid || c != 0) return;
   backward_finish(p, a, b, QuTk, kTQuuk);
 }

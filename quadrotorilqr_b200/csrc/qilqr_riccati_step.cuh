@@ -23,10 +23,17 @@ QD void ld9s(const double *s, double *r) {
   for (int e = 0; e < 9; ++e) r[e] = s[e * RS];
 }
 
-template <int RS, bool DENSEQ = false>
+struct NoRecordHook {
+  static constexpr bool kActive = false;
+  QD void operator()() const {}
+};
+// record_done(): called once the whole warp has made its last read of this knot's record (a kernel with a single
+// record buffer starts the next knot's copy there).
+template <int RS, bool DENSEQ = false, class RecordDone = NoRecordHook>
 QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double *rec, const double *s2Qvv,
                      double *xch, const int c, double *gk_lane, double *gK_lane, const int ii, const int B, double *V0,
-                     double *V1, double *V2, double *V3, double *vx, double *V88, double &QuTk, double &kTQuuk) {
+                     double *V1, double *V2, double *V3, double *vx, double *V88, double &QuTk, double &kTQuuk,
+                     RecordDone record_done = RecordDone()) {
   const double dgz[3] = {rec[R_GZ * RS], rec[(R_GZ + 1) * RS], rec[(R_GZ + 2) * RS]};
   const double ndgz[3] = {-dgz[0], -dgz[1], -dgz[2]};
 
@@ -204,6 +211,11 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
         for (int cc = 0; cc < 3; ++cc) acc = QFMA(X3[3 * s + cc], p.Bu[4 * (1 + cc) + jj], acc);
         Qxu[4 * s + jj] = acc;
       }
+  }
+
+  if (RecordDone::kActive) {
+    __syncwarp();
+    record_done();
   }
 
   // ---------------- step 4: K[:, 3r..3r+2], (K^T Q_uu)[r], v_x'[r] ----------------
