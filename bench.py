@@ -87,7 +87,12 @@ class ClockSampler:
         self.proc = None
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
-        time.sleep(0.25)  # let the first sample arrive before the timed region starts
+        # nvidia-smi takes 0.2 - 2 s to come up (longer on a box with 8 GPUs): wait for its first line, so that it is
+        # already streaming when the (sub-second) timed region starts; only what arrives after this point counts
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < 10.0:
+            time.sleep(0.02)
+        self.mark = len(self.samples)
 
     def stop(self):
         self.stop_flag = True
@@ -98,15 +103,16 @@ class ClockSampler:
                 pass
         if self.thread:
             self.thread.join(timeout=6)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        samples = self.samples[getattr(self, "mark", 0):] or self.samples[-1:]
+        sm = [float(s[0]) for s in samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
         reasons = set()
-        for s in self.samples:
+        for s in samples:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "sm_min_mhz": min(sm) if sm else None, "reasons": sorted(reasons), "samples": len(self.samples)}
+                "sm_min_mhz": min(sm) if sm else None, "reasons": sorted(reasons), "samples": len(samples)}
 
 
 def oracle_config(O, m, opts):

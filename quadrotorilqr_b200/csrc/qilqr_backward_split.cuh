@@ -110,7 +110,7 @@ struct NextRecord {
 // slower, and 9 or 10 resident warps per SM at 224 / 200 registers -- which the smaller footprint would allow -- no
 // faster: profiles/README.md.)
 template <bool DENSEQ>
-__global__ void __launch_bounds__(32) k_riccati_g4(const __grid_constant__ DeviceParams p,
+__global__ void __maxnreg__(255) k_riccati_g4(const __grid_constant__ DeviceParams p,
                                                                        const __grid_constant__ BackwardArgs a, const double *rec_g) {
   using namespace g4;
   constexpr int TILE = tile_doubles(DENSEQ);
