@@ -580,6 +580,27 @@ def main():
         e2e["ctl_same_results"] = bool(np.array_equal(r3, r2))
         e2e["ctl_h2d"] = B * 13 * 8 + N * 4 * 8 + N * 18 * 8
 
+        # ... and with the solved CONTROLS [B][N][4] as the only trajectory output (what a receding-horizon caller
+        # consumes; the states are their rollout from x0): 22 % of the bytes of the full trajectories come back
+        traj_ref = out_host[0][0][:, :, 14:18].clone()
+        uout_host = [[torch.empty((B, N, 4), dtype=torch.float64, pin_memory=True) for _ in range(H)] for _ in range(P)]
+
+        def ctl_out_begin(j, h):
+            solvers[j][h].solve_from_controls(x0_host, u_nom, desired_c, out_controls=uout_host[j][h], want_traj=False,
+                                              results=res_host[j][h], begin_only=True)
+
+        run_pipelined(ctl_out_begin, host_finish, P * H)
+        barrier()
+        t0 = time.perf_counter()
+        run_pipelined(ctl_out_begin, host_finish, e2e_steps, stagger_s)
+        barrier()
+        e2e["cc_t"] = time.perf_counter() - t0
+        r4 = np.frombuffer(res_host[0][0].numpy().tobytes(), dtype=RESULT_DTYPE)
+        e2e["cc_converged"] = int(np.sum((r4["status"] == 1) | (r4["status"] == 2)))
+        e2e["cc_same_results"] = bool(np.array_equal(r4, r2) and torch.equal(uout_host[0][0], traj_ref))
+        e2e["cc_d2h"] = B * N * 4 * 8 + B * 24
+        del traj_ref
+
         # what the host's memory system gives this rank while every rank copies at once: the H2D + D2H traffic of one
         # step (pinned buffers, both directions concurrently) -- the denominator for the end-to-end scaling
         dma_dev = torch.empty((B, N, 18), dtype=torch.float64, device=dev)
@@ -601,7 +622,8 @@ def main():
                         float(max_iter_hit), float(launches), e2e["t"] if e2e else 0.0,
                         float(e2e["converged"]) if e2e else 0.0, e2e["ctl_t"] if e2e else 0.0,
                         float(e2e["ctl_converged"]) if e2e else 0.0,
-                        e2e["dma_gbs_per_direction"] if e2e else 0.0], dtype=torch.float64, device=dev)
+                        e2e["dma_gbs_per_direction"] if e2e else 0.0, e2e["cc_t"] if e2e else 0.0,
+                        float(e2e["cc_converged"]) if e2e else 0.0], dtype=torch.float64, device=dev)
     gathered_converged = None
     if dist is not None:
         mx = vec.clone()
@@ -743,6 +765,12 @@ def main():
             "api": "qilqr_solve_from_controls_host_begin / qilqr_solve_host_finish: x0 [B][13] and one nominal control "
                    "sequence in (this workload's initial trajectories are their open-loop rollout, made on the device), "
                    "full trajectories [B][N][18] out"}
+        line["e2e_controls_in_controls_out"] = {
+            "value": sm[13] / (mx[12] / e2e["steps"]), "unit": UNIT, "ms_per_step": 1e3 * mx[12] / e2e["steps"],
+            "h2d_bytes_per_step": e2e["ctl_h2d"], "d2h_bytes_per_step": e2e["cc_d2h"],
+            "same_results_as_e2e": e2e["cc_same_results"],
+            "api": "qilqr_solve_from_controls_host_begin (out_traj = NULL, out_controls [B][N][4]) / "
+                   "qilqr_solve_host_finish: the solved control sequences and the per-problem results come back"}
         line["host_dma"] = {
             "gbs_per_direction_all_gpus": sm[11], "gbs_per_direction_per_gpu": sm[11] / world,
             "note": "pinned-memory H2D and D2H copies of one step's trajectories, both directions at once, on every rank at "
