@@ -51,3 +51,22 @@ def test_dense_q_backward_pass_and_solve_match_oracle(O, symmetric, monkeypatch)
         assert np.array_equal(r["results"]["status"], o["status"])
         assert np.array_equal(r["results"]["backward_passes"], o["backward_passes"])
         assert np.max(np.abs(r["traj"] - o["traj"])) <= 1e-9 * max(1.0, np.max(np.abs(o["traj"])))
+
+
+def test_diagonal_q_cost_shortcut_is_bit_neutral(monkeypatch):
+    """A diagonal Q lets the running cost skip the off-diagonal products of dx^T Q (DeviceParams::q_diagonal): every
+    skipped term is (+-0) + (+-0), so costs, decisions and trajectories are the same doubles as with the dense chain
+    (QILQR_Q_DIAGONAL=0 forces the dense chain).  The role-specialised rollout and the cost API go through it too."""
+    from quadrotorilqr_b200 import problems
+
+    model, opts = problems.hover_model(), problems.default_options(False)
+    fast = make_solver(model, opts)
+    monkeypatch.setenv("QILQR_Q_DIAGONAL", "0")
+    dense = make_solver(model, opts)
+    monkeypatch.delenv("QILQR_Q_DIAGONAL")
+    B, N = 5000, 40      # above the role-specialised rollout's launch size at first, below it later
+    d, init = batch(fast, model, B, N, seed=11)
+    assert np.array_equal(fast.cost_trajectory(init, d), dense.cost_trajectory(init, d))
+    a, b = fast.solve(init, d, hist_cap=100), dense.solve(init, d, hist_cap=100)
+    assert np.array_equal(a["results"], b["results"])
+    assert np.array_equal(a["traj"], b["traj"]) and np.array_equal(a["cost_history"], b["cost_history"])
