@@ -27,7 +27,13 @@ def test_bench_line_has_the_contract_keys():
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(j["e2e"])
     assert j["e2e"]["value"] > 0 and j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(j["roofline"])
-    assert 0 < j["roofline"]["frac"] < 1.2 and j["roofline"]["peak"] > 10
+    assert 0 < j["roofline"]["frac"] < 2.0 and j["roofline"]["peak"] > 10  # dense-count fraction: > 1 is possible
+    assert 0 < j["roofline"]["executed_frac"] < 1.0
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(j["cpu_baseline"])
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(j["clocks"])
+    assert j["clocks"]["samples"] >= 1 and j["clocks"]["sm_mhz"] > 0     # sampled inside the timed region
+    # the compact entry points give the same results as the full-trajectory call
+    for key in ("e2e_from_controls", "e2e_controls_in_controls_out"):
+        assert j[key]["value"] > 0 and j[key]["same_results_as_e2e"] is True, key
+    assert j["e2e_controls_in_controls_out"]["d2h_bytes_per_step"] < j["e2e"]["d2h_bytes_per_step"] / 4
     assert "workload" in j["config"]
