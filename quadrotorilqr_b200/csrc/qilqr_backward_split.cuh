@@ -3,16 +3,17 @@
 //
 //   k_linearise   one thread per (problem, knot): all knots of all problems are linearised in
 //                 parallel (dynamics blocks, cost gradient, pose block of the Gauss-Newton Hessian)
-//                 into 100-double records, stored as tiles  rec[tile of 8 problems][knot][elem][8]
+//                 into 101-double records, stored as tiles  rec[tile of 8 problems][knot][elem][8]
 //   k_riccati_g4  one warp per tile of 8 problems (4 lanes each): walks the horizon backwards; the
-//                 next knot's 6.4 kB record tile is fetched by a TMA bulk copy
-//                 (cp.async.bulk + mbarrier, double-buffered) while the current knot's Riccati step
-//                 (qilqr_riccati_step.cuh) runs on registers / shared memory.
+//                 next knot's 6.4 kB record tile is fetched by a TMA bulk copy (cp.async.bulk +
+//                 mbarrier) into the one record buffer as soon as the current knot's Riccati step
+//                 (qilqr_riccati_step.cuh) has read the record for the last time, and lands while
+//                 the rest of the step runs on registers / shared memory.
 //
 // Compared with the fused kernel (qilqr_backward_g4.cuh) this removes the Lie-group code and the
 // per-problem record storage from the sequential kernel (smaller code, less shared memory per warp
 // -> more resident warps), makes the scalar linearisation fully parallel, and costs one round trip
-// of the records through HBM (800 B per problem-knot).
+// of the records through HBM (808 B per problem-knot).
 // =============================================================================
 #pragma once
 #ifndef __CUDACC_RTC__
