@@ -45,6 +45,20 @@ __host__ __device__ constexpr int stride(int kpp) {
   return base + ((4 - base % 16) + 16) % 16;
 }
 __host__ __device__ constexpr int smem_doubles(int kpp) { return 8 * stride(kpp) + 36; }
+// The 2*Q_vv table that lanes c = 2, 3 of a quad read while lanes c = 0, 1 read their row group of C_pp from the
+// record.  RS = 1 (records per problem): 36 doubles, row-major.  RS = 8 (record tiles [element][8 problems]): laid
+// out LIKE the C_pp part of a tile -- element (row group g, j) at ((R_CPP_GROUP g + j) * 8 + slot), the same value in
+// all 8 slots -- and quad q reads slot (q + 4) & 7: within each half-warp the table lanes then sit on the 16 banks
+// that the half-warp's record lanes leave free (ncu: the remaining excess wavefronts of the step came from here).
+constexpr int QVV_TILE = (R_CPP_GROUP + 18) * 8;
+template <int RS>
+QD int qvv_group(int g) { return (RS == 1 ? 18 : R_CPP_GROUP) * g * RS; }
+QD void init_qvv_tile(const DeviceParams &p, double *tile, int tid, int nthreads) {
+  for (int e = tid; e < 36 * 8; e += nthreads) {
+    const int slot = e & 7, k = e >> 3, g = k / 18, j = k % 18;  // k: row-major index into the 6x6 block
+    tile[(R_CPP_GROUP * g + j) * 8 + slot] = 2.0 * p.Q[12 * (6 + k / 6) + 6 + k % 6];
+  }
+}
 QD int moff(int I, int J) { return X_M + I * 37 + J * 9; }
 
 QD void ld9(const double *s, double *r) {

@@ -31,7 +31,7 @@ __host__ __device__ constexpr int rect(bool denseq) { return denseq ? 173 : 101;
 // doubles per (tile of 8 problems, knot): 6464 B / 11072 B, multiples of 16
 __host__ __device__ constexpr int tile_doubles(bool denseq) { return rect(denseq) * 8; }
 constexpr int XS = 228;               // exchange stride per problem, = 4 (mod 16)
-__host__ __device__ constexpr int split_smem_doubles(bool denseq) { return tile_doubles(denseq) + 8 * XS + 36 + 2; }
+__host__ __device__ constexpr int split_smem_doubles(bool denseq) { return tile_doubles(denseq) + 8 * XS + QVV_TILE + 2; }
 
 QD uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 QD void mbar_init(uint64_t *bar, int count) {
@@ -126,8 +126,8 @@ __global__ void __maxnreg__(255) k_riccati_g4(const __grid_constant__ DevicePara
   double *bufs = smem;
   double *xch = smem + TILE + q * XS;
   double *s2Qvv = smem + TILE + 8 * XS;
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + 36);
-  for (int e = lane; e < 36; e += 32) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(s2Qvv + QVV_TILE);
+  init_qvv_tile(p, s2Qvv, lane, 32);
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,7 +154,7 @@ __global__ void __maxnreg__(255) k_riccati_g4(const __grid_constant__ DevicePara
     mbar_wait(&mbar[0], phase0);
     phase0 ^= 1;
     g4::NextRecord hook{bufs, i > 0 ? src + size_t(i - 1) * TILE : nullptr, &mbar[0], lane, kBytes};
-    riccati_step<8, DENSEQ, g4::NextRecord>(p, a, bufs + q, s2Qvv, xch, c, gk_lane, gK_lane, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk, hook);
+    riccati_step<8, DENSEQ, g4::NextRecord>(p, a, bufs + q, s2Qvv + ((q + 4) & 7), xch, c, gk_lane, gK_lane, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk, hook);
   }
   if (!valid || c != 0) return;
   backward_finish(p, a, b, QuTk, kTQuuk);

@@ -7,7 +7,7 @@
 //   gk_lane, gK_lane : where this lane's gains go -- gk + c * B + b and gK + 3 c * B + b of the problem (the padding
 //            quads of a last tile shadow the last problem and rewrite identical values; quads of the persistent
 //            tail kernel whose problem is not in its backward pass get a scratch array)
-//   s2Qvv  : 2*Q_vv (6x6), dense
+//   s2Qvv  : 2*Q_vv (6x6): dense for RS = 1; for RS = 8 the quad's slot of the tile-like table (g4::QVV_TILE)
 //   xch    : this problem's exchange area (g4::XCH doubles)
 //   V0..V3 : the lane's column block c of V_xx (in/out);  vx: v_x (replicated, in/out)
 //   V88    : V_xx[8:12, 8:12] (replicated, in/out) -- all that Q_uu = C_uu + B^T V_xx B needs
@@ -142,8 +142,8 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     const bool lo = c < 2;
     if (DENSEQ) {
       const double *srcA = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (rec + (R_CVP + 18 * (c - 2)) * RS);
-      const double *srcB = lo ? (rec + (R_CPV + 18 * c) * RS) : (s2Qvv + 18 * (c - 2));
-      const int sB = lo ? RS : 1;  // the record is strided, the 2*Q_vv table is dense
+      const double *srcB = lo ? (rec + (R_CPV + 18 * c) * RS) : (s2Qvv + qvv_group<RS>(c - 2));
+      constexpr int sB = RS;  // record and table have the same element stride
 #pragma unroll
       for (int ri = 0; ri < 3; ++ri)
 #pragma unroll
@@ -156,8 +156,8 @@ QD void riccati_step(const DeviceParams &p, const BackwardArgs &a, const double 
     } else {
       // Lanes 0, 1 own pose rows [C_pp | 0], lanes 2, 3 velocity rows [0 | 2 Q_vv]: one 3x6 source per lane, and the
       // zero half enters as source * 0.0 inside the fused add below instead of a select per element.
-      const double *src = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (s2Qvv + 18 * (c - 2));
-      const int sst = lo ? RS : 1;
+      const double *src = lo ? (rec + (R_CPP + R_CPP_GROUP * c) * RS) : (s2Qvv + qvv_group<RS>(c - 2));
+      constexpr int sst = RS;  // record and table have the same element stride
 #pragma unroll
       for (int ri = 0; ri < 3; ++ri)
 #pragma unroll

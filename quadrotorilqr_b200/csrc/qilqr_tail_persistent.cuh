@@ -29,7 +29,7 @@ namespace qilqr {
 
 namespace tp {
 __host__ __device__ constexpr int smem_doubles(bool denseq) {
-  return 2 * g4::tile_doubles(denseq) + 8 * g4::XS + 36 + (2 * 7 + 6 + 4) * 32;
+  return 2 * g4::tile_doubles(denseq) + 8 * g4::XS + g4::QVV_TILE + (2 * 7 + 6 + 4) * 32;
 }
 }  // namespace tp
 
@@ -43,15 +43,15 @@ __global__ void __launch_bounds__(96, 1) k_tail_persistent(const __grid_constant
   double *bufs = smem;
   double *xch_all = smem + 2 * TILE;
   double *s2Qvv = xch_all + 8 * XS;
-  double(*s_pose)[7][32] = reinterpret_cast<double(*)[7][32]>(s2Qvv + 36);
-  double(*s_vel)[32] = reinterpret_cast<double(*)[32]>(s2Qvv + 36 + 2 * 7 * 32);
-  double(*s_u)[32] = reinterpret_cast<double(*)[32]>(s2Qvv + 36 + (2 * 7 + 6) * 32);
+  double(*s_pose)[7][32] = reinterpret_cast<double(*)[7][32]>(s2Qvv + QVV_TILE);
+  double(*s_vel)[32] = reinterpret_cast<double(*)[32]>(s2Qvv + QVV_TILE + 2 * 7 * 32);
+  double(*s_u)[32] = reinterpret_cast<double(*)[32]>(s2Qvv + QVV_TILE + (2 * 7 + 6) * 32);
   __shared__ int s_prob[8], s_act[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, N = pr.N, B = pr.B, Bd = pr.Bd;
   double *rec_tile = rec_g + size_t(tile) * N * TILE;
-  for (int e = tid; e < 36; e += 96) s2Qvv[e] = 2.0 * p.Q[12 * (6 + e / 6) + 6 + e % 6];
+  init_qvv_tile(p, s2Qvv, tid, 96);
   // the 8 problems of this tile; slots beyond n shadow the last problem and never write
   if (tid < 8) {
     const int idx = min(tile * 8 + tid, n - 1);
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(96, 1) k_tail_persistent(const __grid_constant
           // (quads whose problem is not in its backward pass sweep stale records: their gains go to a scratch array
           //  laid out like the real one)
           double *gk0 = act ? pr.gk : scratch_gains, *gK0 = act ? pr.gK : scratch_gains + size_t(N) * 4 * B;
-          riccati_step<8, DENSEQ>(p, ba, bufs + s * TILE + q, s2Qvv, xch_all + q * XS, c, gk0 + size_t(c) * B + t,
+          riccati_step<8, DENSEQ>(p, ba, bufs + s * TILE + q, s2Qvv + ((q + 4) & 7), xch_all + q * XS, c, gk0 + size_t(c) * B + t,
                                   gK0 + size_t(3 * c) * B + t, i, B, V0, V1, V2, V3, vx, V88, QuTk, kTQuuk);
         } else if (i > 0) {
           for (int e = tid - 32; e < TILE; e += 64) bufs[(s ^ 1) * TILE + e] = rec_tile[size_t(i - 1) * TILE + e];
